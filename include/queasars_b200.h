@@ -1,0 +1,168 @@
+/*
+ * queasars_b200 -- C-ABI of the B200 (sm_100a) statevector evaluation engine behind QUEASARS' EVQE loop.
+ *
+ * Plain C, plain pointers and sizes, no torch / C++ types.  The reference (DLR-RB/QUEASARS v0.3.2) is pure
+ * Python and delegates this whole path to a Qiskit Estimator/Sampler primitive, so there is no existing
+ * FFI; each entry point below names the reference interface whose work it takes over.  Paths are relative
+ * to the reference checkout; [upstream] marks behaviour of un-vendored qiskit 2.4.2.
+ *
+ * Conventions
+ *   - little-endian qubits: qubit q is bit q of the amplitude index (utility/pauli_strings.py:38-41)
+ *   - statevectors are interleaved (re, im) complex128 (QB_C128) or complex64 (QB_C64)
+ *   - every function returns QB_OK (0) or a negative error code; qb_last_error() gives the message of the
+ *     last failure on the calling thread.  Nothing falls back to the CPU: without a CUDA device the
+ *     compute entry points fail with QB_ERR_CUDA.
+ *   - host buffers are owned by the caller and may be pageable; entry points are thread-safe per context.
+ */
+#ifndef QUEASARS_B200_H
+#define QUEASARS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_OK 0
+#define QB_ERR_INVALID (-1)
+#define QB_ERR_CUDA (-2)
+#define QB_ERR_MEMORY (-3)
+#define QB_ERR_NOT_FOUND (-4)
+
+#define QB_C128 0
+#define QB_C64 1
+
+#define QB_TILE_BITS 12 /* amplitudes per CTA tile = 2^12 */
+#define QB_REG_BITS 4   /* amplitudes per thread   = 2^4  */
+#define QB_LOW_BITS 4   /* lowest qubits always inside the tile (256 B contiguous runs for c128) */
+
+/* operand-position kinds inside a pass (see queasars_b200/schedule.py) */
+#define QB_K_NONE 0
+#define QB_K_REG 1    /* pos = index into the pass's reg_bits            */
+#define QB_K_THREAD 2 /* pos = tile-local bit held in the thread index   */
+#define QB_K_EXT 3    /* pos = global qubit outside the tile             */
+
+#define QB_OP_DENSE 0 /* e^{i gamma} U(theta,phi,lam) on target [, control]            */
+#define QB_OP_DIAG 1  /* diag(e^{i gamma}, e^{i(gamma+lam)}) on target [, control]     */
+
+/* --- sweep program records (flat arrays produced by the host-side planner) ------------------------- */
+typedef struct qb_sweep {
+    int32_t tile_qubits[16]; /* QB_TILE_BITS entries used, ascending; tile-local bit i <-> this qubit */
+    int32_t pass_begin, pass_end;
+    int32_t reserved[2];
+} qb_sweep;
+
+typedef struct qb_pass {
+    int32_t reg_bits[4]; /* tile-local bit positions held in registers */
+    int32_t op_begin, op_end;
+    uint8_t thread_bits[8]; /* tile-local bit carried by thread-index bit 0..7 (the 8 non-register bits) */
+} qb_pass;
+
+typedef struct qb_pass_op {
+    int32_t op_index; /* index into the circuit's op table (selects the bound 2x2 matrix) */
+    uint8_t kind;     /* QB_OP_*  */
+    uint8_t tgt_kind, tgt_pos;
+    uint8_t ctrl_kind, ctrl_pos;
+    uint8_t pad[3];
+} qb_pass_op;
+
+/* angle sources of one op: value_j = cnst[j] + coeff[j] * params[slot[j]]  (slot < 0: constant);
+ * j = 0..3 -> gamma, theta, phi, lam.  This is where the flat parameter vector of
+ * circuit_evaluation.py:205-207 is bound ([upstream] EstimatorPub.coerce order = sorted parameter names). */
+typedef struct qb_op_angles {
+    int32_t slot[4];
+    double coeff[4];
+    double cnst[4];
+    int32_t kind;
+    int32_t pad;
+} qb_op_angles;
+
+typedef struct qb_context qb_context;
+
+/* --- context ---------------------------------------------------------------------------------------- */
+/* One engine per (process, device).  `stream` = an existing cudaStream_t to launch on (e.g. torch's), or
+ * NULL to let the context create its own non-blocking stream. */
+int qb_context_create(int device, void* stream, qb_context** out);
+int qb_context_destroy(qb_context* ctx);
+const char* qb_last_error(void);
+/* cudaStream_t the context launches on (for CUDA-event timing by the caller). */
+void* qb_context_stream(qb_context* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t qb_context_launch_count(qb_context* ctx);
+/* Upper bound for statevector workspace (bytes); 0 = 80 % of the device memory free at creation. */
+int qb_context_set_workspace_limit(qb_context* ctx, uint64_t bytes);
+int qb_context_synchronize(qb_context* ctx);
+
+/* --- plans: a parsed + scheduled circuit --------------------------------------------------------------
+ * Replaces TranspilingEstimatorV2/SamplerV2.run's per-call PassManager.run
+ * (circuit_evaluation/transpiling_primitives.py:47, 73-80) and the upstream per-call circuit binding:
+ * the circuit is compiled once, parameters are bound on the device at evaluation time. */
+int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int n_params,
+                   int n_ops, const qb_op_angles* ops,
+                   int n_sweeps, const qb_sweep* sweeps,
+                   int n_passes, const qb_pass* passes,
+                   int n_pass_ops, const qb_pass_op* pass_ops,
+                   int64_t* plan_id);
+int qb_plan_destroy(qb_context* ctx, int64_t plan_id);
+
+/* --- Hamiltonians ---------------------------------------------------------------------------------------
+ * H = sum_t (coeff_re[t] + i coeff_im[t]) * P_t with P_t = i^{popcount(x&z)} X^{x_mask} Z^{z_mask}
+ * (the SparsePauliOp handed to OperatorCircuitEvaluator, circuit_evaluation.py:181-198).
+ * build_table != 0 precomputes the diagonal part E(k) = sum_t c_t (-1)^{popcount(k & z_t)} as an fp64 table
+ * of 2^n entries ([upstream] _evaluate_sparsepauli / sampled_expectation_value semantics). */
+int qb_hamiltonian_create(qb_context* ctx, int n_qubits, int n_terms,
+                          const uint64_t* x_masks, const uint64_t* z_masks,
+                          const double* coeff_re, const double* coeff_im,
+                          int build_table, int64_t* ham_id);
+int qb_hamiltonian_destroy(qb_context* ctx, int64_t ham_id);
+/* E(k) for a list of basis states (sampler routes: expectation_calculation.py:60-66). */
+int qb_hamiltonian_diag_energies(qb_context* ctx, int64_t ham_id, int64_t n_states,
+                                 const uint64_t* states, double* out_energies);
+
+/* --- batched evaluation ---------------------------------------------------------------------------------
+ * One call = the batched submission of a generation's circuits: entry i evaluates plan_ids[i] with the
+ * parameter vector params[param_offsets[i] .. param_offsets[i+1]).
+ *
+ * qb_evaluate_expectation  <->  OperatorCircuitEvaluator.evaluate_circuits (circuit_evaluation.py:200-215)
+ *   + [upstream] StatevectorEstimator._run_pub with precision = 0:  out[i] = Re <psi_i|H|psi_i>.
+ * qb_sample  <->  measure_quasi_distributions (circuit_evaluation.py:29-59) + [upstream]
+ *   StatevectorSampler._run_pub / Generator.choice: out_indices[i*shots + s] =
+ *   searchsorted(cumsum(|psi_i|^2)/sum, uniforms[i*shots + s], side='right').
+ * qb_statevector: amplitudes of one bound circuit as complex128 (testing / debugging). */
+int qb_evaluate_expectation(qb_context* ctx, int batch, const int64_t* plan_ids,
+                            const double* params, const int64_t* param_offsets,
+                            int64_t ham_id, double* out_values);
+int qb_sample(qb_context* ctx, int batch, const int64_t* plan_ids,
+              const double* params, const int64_t* param_offsets,
+              int shots, const double* uniforms, int64_t* out_indices);
+int qb_statevector(qb_context* ctx, int64_t plan_id, const double* params, int n_params,
+                   double* out_re_im /* 2 * 2^n doubles */);
+
+/* --- resident batches (benchmarks, optimizer inner loops) ---------------------------------------------
+ * Same work as qb_evaluate_expectation split into its host<->device and device-only parts so the
+ * device-resident throughput can be timed separately from the end-to-end call. */
+int qb_batch_create(qb_context* ctx, int batch, const int64_t* plan_ids, int64_t ham_id, int64_t* batch_id);
+int qb_batch_set_params(qb_context* ctx, int64_t batch_id, const double* params, const int64_t* param_offsets);
+int qb_batch_run(qb_context* ctx, int64_t batch_id);   /* asynchronous on the context's stream */
+int qb_batch_read(qb_context* ctx, int64_t batch_id, double* out_values); /* synchronises */
+int qb_batch_destroy(qb_context* ctx, int64_t batch_id);
+/* sweep launches / algorithmic bytes of one qb_batch_run (for roofline accounting) */
+int qb_batch_stats(qb_context* ctx, int64_t batch_id, int64_t* n_sweep_launches, int64_t* n_state_sweeps,
+                   int64_t* sweep_bytes, int64_t* n_kernel_launches);
+
+/* --- device-pointer entry points (parity tests, sharded multi-GPU path) -------------------------------
+ * Operate on a caller-owned device statevector of 2^n_local amplitudes.  `index_offset` is OR-ed into the
+ * amplitude index seen by QB_K_EXT operands and by the diagonal table lookup, so a rank holding the shard
+ * with global-qubit bits `rank << n_local` evaluates controls on global qubits correctly. */
+int qb_apply_plan_device(qb_context* ctx, int64_t plan_id, const double* params_host, int n_params,
+                         void* d_state, int init_zero_state, uint64_t index_offset);
+int qb_expectation_device(qb_context* ctx, int64_t ham_id, int dtype, int n_local, const void* d_state,
+                          uint64_t index_offset, double* out_value);
+
+/* layout self-check for language bindings: sizeof() of the four records above */
+void qb_record_sizes(int32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUEASARS_B200_H */

@@ -1,0 +1,106 @@
+"""ctypes binding of the C-ABI in include/queasars_b200.h.  There is no CPU fallback: if the shared
+library is missing this raises, and every compute call needs a CUDA device."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+import numpy as np
+
+from . import schedule
+from ._build import LIB_PATH
+
+QB_OK = 0
+QB_C128, QB_C64 = 0, 1
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class QbError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"queasars_b200 native error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def _declare(lib):
+    P = POINTER
+    sigs = {
+        "qb_context_create": [c_int, c_void_p, P(c_void_p)],
+        "qb_context_destroy": [c_void_p],
+        "qb_context_stream": [c_void_p],
+        "qb_context_launch_count": [c_void_p],
+        "qb_context_set_workspace_limit": [c_void_p, c_uint64],
+        "qb_context_synchronize": [c_void_p],
+        "qb_plan_create": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, P(c_int64)],
+        "qb_plan_destroy": [c_void_p, c_int64],
+        "qb_hamiltonian_create": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, P(c_int64)],
+        "qb_hamiltonian_destroy": [c_void_p, c_int64],
+        "qb_hamiltonian_diag_energies": [c_void_p, c_int64, c_int64, c_void_p, c_void_p],
+        "qb_evaluate_expectation": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
+        "qb_sample": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+        "qb_statevector": [c_void_p, c_int64, c_void_p, c_int, c_void_p],
+        "qb_batch_create": [c_void_p, c_int, c_void_p, c_int64, P(c_int64)],
+        "qb_batch_set_params": [c_void_p, c_int64, c_void_p, c_void_p],
+        "qb_batch_run": [c_void_p, c_int64],
+        "qb_batch_read": [c_void_p, c_int64, c_void_p],
+        "qb_batch_destroy": [c_void_p, c_int64],
+        "qb_batch_stats": [c_void_p, c_int64, P(c_int64), P(c_int64), P(c_int64), P(c_int64)],
+        "qb_apply_plan_device": [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_uint64],
+        "qb_expectation_device": [c_void_p, c_int64, c_int, c_int, c_void_p, c_uint64, P(c_double)],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    lib.qb_context_stream.restype = c_void_p
+    lib.qb_context_launch_count.restype = c_int64
+    lib.qb_last_error.argtypes = []
+    lib.qb_last_error.restype = c_char_p
+    lib.qb_record_sizes.argtypes = [P(c_int32)]
+    lib.qb_record_sizes.restype = None
+    return sigs
+
+
+EXPORTED_SYMBOLS = (
+    "qb_context_create qb_context_destroy qb_last_error qb_context_stream qb_context_launch_count "
+    "qb_context_set_workspace_limit qb_context_synchronize qb_plan_create qb_plan_destroy qb_hamiltonian_create "
+    "qb_hamiltonian_destroy qb_hamiltonian_diag_energies qb_evaluate_expectation qb_sample qb_statevector "
+    "qb_batch_create qb_batch_set_params qb_batch_run qb_batch_read qb_batch_destroy qb_batch_stats "
+    "qb_apply_plan_device qb_expectation_device qb_record_sizes"
+).split()
+
+
+def load():
+    """Load (once) and return the native library; raises NativeLibraryError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  queasars_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    _declare(lib)
+    sizes = (c_int32 * 4)()
+    lib.qb_record_sizes(sizes)
+    expect = [schedule.SWEEP_DTYPE.itemsize, schedule.PASS_DTYPE.itemsize, schedule.PASSOP_DTYPE.itemsize, schedule.ANGLE_DTYPE.itemsize]
+    if list(sizes) != expect:
+        raise NativeLibraryError(f"record layout mismatch between schedule.py {expect} and the native library {list(sizes)}")
+    _lib = lib
+    return lib
+
+
+def check(code: int):
+    if code != QB_OK:
+        raise QbError(code, load().qb_last_error().decode("utf-8", "replace"))
+
+
+def ptr(arr: np.ndarray):
+    return arr.ctypes.data_as(c_void_p)

@@ -1,0 +1,841 @@
+// C-ABI implementation (include/queasars_b200.h): contexts, plans, Hamiltonians, batched evaluation.
+// No CPU fallback: every compute entry point needs a CUDA device and fails with QB_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "qb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define QB_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t qb_e_ = (call);                                                                        \
+        if (qb_e_ != cudaSuccess)                                                                          \
+            return fail(QB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(qb_e_));               \
+    } while (0)
+
+#define QB_TRY(call)                 \
+    do {                             \
+        int qb_r_ = (call);          \
+        if (qb_r_ != QB_OK) return qb_r_; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return QB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(QB_ERR_MEMORY, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+        }
+        cap = bytes;
+        return QB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {  // pinned staging
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return QB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(bytes, 1 << 16);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(QB_ERR_MEMORY, std::string("cudaHostAlloc failed: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return QB_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Plan {
+    int n_qubits = 0, n_eff = 0, dtype = 0, n_params = 0, n_ops = 0, n_sweeps = 0;
+    DevBuf sweeps, passes, pass_ops, angles;
+    ~Plan() { sweeps.release(), passes.release(), pass_ops.release(), angles.release(); }
+};
+
+struct Group {
+    uint64_t xmask = 0;
+    int n_terms = 0;
+    DevBuf z, wr, wi;
+};
+
+struct Ham {
+    int n_qubits = 0;
+    int n_diag = 0;       // number of z-only terms (device arrays diag_z / diag_c, real coefficients)
+    bool diagonal = true;  // no x-mask anywhere
+    DevBuf diag_z, diag_c;
+    std::vector<std::unique_ptr<Group>> groups;  // x == 0 group first (if any), complex weights
+    DevBuf table;
+    int table_n_eff = 0;
+    ~Ham() {
+        diag_z.release(), diag_c.release(), table.release();
+        for (auto& g : groups) g->z.release(), g->wr.release(), g->wi.release();
+    }
+};
+
+// A set of circuit evaluations resident on the device.
+struct DeviceBatch {
+    int batch = 0, n_eff = 0, n_qubits = 0, dtype = 0, max_sweeps = 0;
+    std::vector<int> order;   // sorted position -> caller index (descending sweep count)
+    std::vector<int> active;  // active[s] = number of entries with more than s sweeps
+    std::vector<qb::BatchEntry> h_entries;
+    std::vector<int64_t> param_begin;  // per caller index, offset into the params buffer
+    int64_t total_params = 0, total_ops = 0;
+    const Ham* ham = nullptr;
+    bool fuse_expect = false;
+    size_t n_tiles = 0, partial_stride = 0;
+    int64_t n_state_sweeps = 0, launches_per_run = 0;
+    DevBuf entries, params, matrices, partials, out, states;
+    bool owns_states = true;
+    ~DeviceBatch() {
+        entries.release(), params.release(), matrices.release(), partials.release(), out.release();
+        if (owns_states) states.release();
+    }
+};
+
+}  // namespace
+
+struct qb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    uint64_t workspace_limit = 0;
+    int64_t launches = 0;
+    int64_t next_id = 1;
+    std::mutex mu;
+    std::map<int64_t, std::unique_ptr<Plan>> plans;
+    std::map<int64_t, std::unique_ptr<Ham>> hams;
+    std::map<int64_t, std::unique_ptr<DeviceBatch>> batches;
+    HostBuf pin_in, pin_out;
+    cudaEvent_t pin_in_done = nullptr;  // last H2D copy out of pin_in
+    DevBuf scratch;                     // uniforms / indices / chunk sums / single-state partials
+    DeviceBatch oneshot;                // buffers reused by the one-shot entry points (no per-call cudaMalloc)
+};
+
+namespace {
+
+size_t amp_bytes(int dtype) { return dtype == QB_C128 ? 16 : 8; }
+
+int set_device(qb_context* ctx) {
+    QB_CUDA(cudaSetDevice(ctx->device));
+    return QB_OK;
+}
+
+template <typename K> int configure_kernel(K kernel, size_t smem) {
+    QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    return QB_OK;
+}
+
+int check_launch(qb_context* ctx, const char* what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QB_ERR_CUDA, std::string(what) + " launch failed: " + cudaGetErrorString(e));
+    return QB_OK;
+}
+
+int upload(qb_context* ctx, DevBuf& dst, const void* src, size_t bytes) {
+    QB_TRY(dst.reserve(std::max<size_t>(bytes, 16)));
+    if (bytes) QB_CUDA(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return QB_OK;
+}
+
+Plan* find_plan(qb_context* ctx, int64_t id) {
+    auto it = ctx->plans.find(id);
+    return it == ctx->plans.end() ? nullptr : it->second.get();
+}
+
+Ham* find_ham(qb_context* ctx, int64_t id) {
+    auto it = ctx->hams.find(id);
+    return it == ctx->hams.end() ? nullptr : it->second.get();
+}
+
+// ---- batch assembly -------------------------------------------------------------------------------
+int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_ids, const Ham* ham, void* external_state,
+                int init_zero, uint64_t index_offset) {
+    if (batch <= 0) return fail(QB_ERR_INVALID, "batch must be positive");
+    std::vector<Plan*> plans(batch);
+    for (int i = 0; i < batch; ++i) {
+        plans[i] = find_plan(ctx, plan_ids[i]);
+        if (!plans[i]) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[i]));
+        if (plans[i]->n_eff != plans[0]->n_eff || plans[i]->dtype != plans[0]->dtype || plans[i]->n_qubits != plans[0]->n_qubits)
+            return fail(QB_ERR_INVALID, "all plans of one batch must share qubit count and dtype");
+    }
+    b.batch = batch;
+    b.n_eff = plans[0]->n_eff;
+    b.n_qubits = plans[0]->n_qubits;
+    b.dtype = plans[0]->dtype;
+    b.ham = ham;
+    if (ham && ham->n_qubits != b.n_qubits)
+        return fail(QB_ERR_INVALID, "Hamiltonian acts on " + std::to_string(ham->n_qubits) + " qubits, circuits on " + std::to_string(b.n_qubits));
+    b.fuse_expect = ham && ham->diagonal && ham->table.p && ham->table_n_eff == b.n_eff && index_offset == 0;
+    b.n_tiles = size_t(1) << (b.n_eff - qb::kTileBits);
+    b.partial_stride = std::max<size_t>(b.n_tiles, 1024);
+
+    b.order.resize(batch);
+    std::iota(b.order.begin(), b.order.end(), 0);
+    std::stable_sort(b.order.begin(), b.order.end(), [&](int x, int y) { return plans[x]->n_sweeps > plans[y]->n_sweeps; });
+    b.max_sweeps = plans[b.order[0]]->n_sweeps;
+    b.active.assign(b.max_sweeps, 0);
+    b.param_begin.assign(batch + 1, 0);
+    std::vector<int64_t> op_begin(batch + 1, 0);
+    b.n_state_sweeps = 0;
+    for (int i = 0; i < batch; ++i) {
+        b.param_begin[i + 1] = b.param_begin[i] + plans[i]->n_params;
+        op_begin[i + 1] = op_begin[i] + plans[i]->n_ops;
+        for (int s = 0; s < plans[i]->n_sweeps; ++s) b.active[s]++;
+        b.n_state_sweeps += plans[i]->n_sweeps;
+    }
+    b.total_params = b.param_begin[batch];
+    b.total_ops = op_begin[batch];
+
+    const size_t state_bytes = (size_t(1) << b.n_eff) * amp_bytes(b.dtype);
+    if (external_state) {
+        if (batch != 1) return fail(QB_ERR_INVALID, "external state needs batch == 1");
+        b.owns_states = false;
+        b.states.p = external_state;
+    } else {
+        const size_t need = state_bytes * size_t(batch);
+        if (ctx->workspace_limit && need > ctx->workspace_limit)
+            return fail(QB_ERR_MEMORY, "batch needs " + std::to_string(need) + " bytes of statevector workspace, limit is " +
+                                           std::to_string(ctx->workspace_limit));
+        QB_TRY(b.states.reserve(need));
+    }
+    QB_TRY(b.params.reserve(std::max<size_t>(sizeof(double) * size_t(b.total_params), 16)));
+    QB_TRY(b.matrices.reserve(std::max<size_t>(sizeof(double) * 8 * size_t(b.total_ops), 64)));
+    QB_TRY(b.partials.reserve(sizeof(double) * b.partial_stride * size_t(batch)));
+    QB_TRY(b.out.reserve(sizeof(double) * size_t(batch)));
+
+    b.h_entries.resize(batch);
+    for (int pos = 0; pos < batch; ++pos) {
+        const int i = b.order[pos];
+        const Plan* pl = plans[i];
+        qb::BatchEntry& en = b.h_entries[pos];
+        en.sweeps = pl->sweeps.as<qb_sweep>();
+        en.passes = pl->passes.as<qb_pass>();
+        en.pass_ops = pl->pass_ops.as<qb_pass_op>();
+        en.angles = pl->angles.as<qb_op_angles>();
+        en.params = b.params.as<double>() + b.param_begin[i];
+        en.matrices = b.matrices.as<double>() + 8 * op_begin[i];
+        en.state = static_cast<unsigned char*>(b.states.p) + state_bytes * size_t(pos);
+        en.diag_table = b.fuse_expect ? ham->table.as<double>() : nullptr;
+        en.partials = b.partials.as<double>() + b.partial_stride * size_t(pos);
+        en.n_sweeps = pl->n_sweeps;
+        en.n_ops = pl->n_ops;
+        en.n_params = pl->n_params;
+        en.init_zero = init_zero;
+        en.index_offset = index_offset;
+    }
+    QB_TRY(upload(ctx, b.entries, b.h_entries.data(), sizeof(qb::BatchEntry) * size_t(batch)));
+    return QB_OK;
+}
+
+int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, const int64_t* param_offsets) {
+    if (b.total_params == 0) return QB_OK;
+    QB_CUDA(cudaEventSynchronize(ctx->pin_in_done));
+    QB_TRY(ctx->pin_in.reserve(sizeof(double) * size_t(b.total_params)));
+    double* stage = static_cast<double*>(ctx->pin_in.p);
+    for (int i = 0; i < b.batch; ++i) {
+        const int64_t n = b.param_begin[i + 1] - b.param_begin[i];
+        if (param_offsets[i + 1] - param_offsets[i] != n)
+            return fail(QB_ERR_INVALID, "entry " + std::to_string(i) + ": got " + std::to_string(param_offsets[i + 1] - param_offsets[i]) +
+                                            " parameter values, circuit has " + std::to_string(n) + " parameters");
+        std::memcpy(stage + b.param_begin[i], params + param_offsets[i], sizeof(double) * size_t(n));
+    }
+    QB_CUDA(cudaMemcpyAsync(b.params.p, stage, sizeof(double) * size_t(b.total_params), cudaMemcpyHostToDevice, ctx->stream));
+    QB_CUDA(cudaEventRecord(ctx->pin_in_done, ctx->stream));
+    return QB_OK;
+}
+
+template <typename T> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b) {
+    const size_t smem = qb::sweep_smem_bytes<T>();
+    for (int s = 0; s < b.max_sweeps; ++s) {
+        dim3 grid(unsigned(b.n_tiles), unsigned(b.active[s]));
+        qb::sweep_kernel<T><<<grid, qb::kThreads, smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
+        QB_TRY(check_launch(ctx, "sweep_kernel"));
+    }
+    return QB_OK;
+}
+
+int launch_circuits(qb_context* ctx, DeviceBatch& b) {
+    qb::bind_kernel<<<b.batch, 128, 0, ctx->stream>>>(b.entries.as<qb::BatchEntry>());
+    QB_TRY(check_launch(ctx, "bind_kernel"));
+    return b.dtype == QB_C128 ? launch_sweeps_t<double>(ctx, b) : launch_sweeps_t<float>(ctx, b);
+}
+
+// expectation of one resident state with the generic (non-fused) kernels; result accumulated into d_out[0]
+template <typename T>
+int expectation_state_t(qb_context* ctx, const Ham& ham, const void* d_state, int n_eff, uint64_t index_offset, double* d_partials,
+                        double* d_out) {
+    using C = typename qb::Cx<T>::type;
+    const uint64_t size = uint64_t(1) << n_eff;
+    const int blocks = int(std::min<uint64_t>(1024, std::max<uint64_t>(1, size / 256)));
+    bool first = true;
+    if (ham.table.p && ham.table_n_eff == n_eff && index_offset == 0) {
+        qb::expect_table_kernel<T><<<blocks, 256, 0, ctx->stream>>>(static_cast<const C*>(d_state), ham.table.as<double>(), size, d_partials);
+        QB_TRY(check_launch(ctx, "expect_table_kernel"));
+        qb::reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(d_partials, blocks, blocks, d_out, 0);
+        QB_TRY(check_launch(ctx, "reduce_partials_kernel"));
+        first = false;
+    }
+    for (const auto& g : ham.groups) {
+        if (g->xmask == 0 && !first) continue;  // diagonal part already taken from the table
+        if (g->xmask >> n_eff) return fail(QB_ERR_INVALID, "Pauli term flips a qubit outside the local statevector");
+        const size_t smem = size_t(g->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double));
+        qb::expect_group_kernel<T><<<blocks, 256, smem, ctx->stream>>>(static_cast<const C*>(d_state), size, index_offset, g->xmask,
+                                                                       g->z.as<uint64_t>(), g->wr.as<double>(), g->wi.as<double>(),
+                                                                       g->n_terms, d_partials);
+        QB_TRY(check_launch(ctx, "expect_group_kernel"));
+        qb::reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(d_partials, blocks, blocks, d_out, first ? 0 : 1);
+        QB_TRY(check_launch(ctx, "reduce_partials_kernel"));
+        first = false;
+    }
+    if (first) QB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream));
+    return QB_OK;
+}
+
+int launch_expectation(qb_context* ctx, DeviceBatch& b) {
+    if (!b.ham) return fail(QB_ERR_INVALID, "batch was created without a Hamiltonian");
+    if (b.fuse_expect) {
+        qb::reduce_partials_kernel<<<b.batch, 256, 0, ctx->stream>>>(b.partials.as<double>(), int64_t(b.partial_stride), int64_t(b.n_tiles),
+                                                                      b.out.as<double>(), 0);
+        return check_launch(ctx, "reduce_partials_kernel");
+    }
+    const size_t state_bytes = (size_t(1) << b.n_eff) * amp_bytes(b.dtype);
+    for (int pos = 0; pos < b.batch; ++pos) {
+        const void* st = static_cast<unsigned char*>(b.states.p) + state_bytes * size_t(pos);
+        double* part = b.partials.as<double>() + b.partial_stride * size_t(pos);
+        double* out = b.out.as<double>() + pos;
+        if (b.dtype == QB_C128) QB_TRY(expectation_state_t<double>(ctx, *b.ham, st, b.n_eff, 0, part, out));
+        else QB_TRY(expectation_state_t<float>(ctx, *b.ham, st, b.n_eff, 0, part, out));
+    }
+    return QB_OK;
+}
+
+int batch_read(qb_context* ctx, DeviceBatch& b, double* out_values) {
+    QB_TRY(ctx->pin_out.reserve(sizeof(double) * size_t(b.batch)));
+    QB_CUDA(cudaMemcpyAsync(ctx->pin_out.p, b.out.p, sizeof(double) * size_t(b.batch), cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double* sorted = static_cast<const double*>(ctx->pin_out.p);
+    for (int pos = 0; pos < b.batch; ++pos) out_values[b.order[pos]] = sorted[pos];
+    return QB_OK;
+}
+
+size_t max_batch_for(qb_context* ctx, const Plan* pl) {
+    const size_t state_bytes = (size_t(1) << pl->n_eff) * amp_bytes(pl->dtype);
+    size_t limit = ctx->workspace_limit;
+    if (!limit) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
+        limit = free_b / 10 * 8;
+    }
+    return std::max<size_t>(1, limit / state_bytes);
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* qb_last_error(void) { return g_last_error.c_str(); }
+
+void qb_record_sizes(int32_t out[4]) {
+    out[0] = int32_t(sizeof(qb_sweep));
+    out[1] = int32_t(sizeof(qb_pass));
+    out[2] = int32_t(sizeof(qb_pass_op));
+    out[3] = int32_t(sizeof(qb_op_angles));
+}
+
+int qb_context_create(int device, void* stream, qb_context** out) {
+    if (!out) return fail(QB_ERR_INVALID, "out is null");
+    int count = 0;
+    QB_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(QB_ERR_INVALID, "no CUDA device " + std::to_string(device));
+    QB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(QB_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                     "; this library is built for sm_100a (B200) only");
+    auto ctx = std::make_unique<qb_context>();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        QB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->owns_stream = true;
+    }
+    QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_in_done, cudaEventDisableTiming));
+    QB_TRY(configure_kernel(qb::sweep_kernel<double>, qb::sweep_smem_bytes<double>()));
+    QB_TRY(configure_kernel(qb::sweep_kernel<float>, qb::sweep_smem_bytes<float>()));
+    *out = ctx.release();
+    return QB_OK;
+}
+
+int qb_context_destroy(qb_context* ctx) {
+    if (!ctx) return QB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->batches.clear();
+    ctx->plans.clear();
+    ctx->hams.clear();
+    ctx->pin_in.release(), ctx->pin_out.release(), ctx->scratch.release();
+    if (ctx->pin_in_done) cudaEventDestroy(ctx->pin_in_done);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return QB_OK;
+}
+
+void* qb_context_stream(qb_context* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+
+int64_t qb_context_launch_count(qb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int qb_context_set_workspace_limit(qb_context* ctx, uint64_t bytes) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    ctx->workspace_limit = bytes;
+    return QB_OK;
+}
+
+int qb_context_synchronize(qb_context* ctx) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    QB_TRY(set_device(ctx));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QB_OK;
+}
+
+// ---- plans ------------------------------------------------------------------------------------------
+int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int n_params, int n_ops, const qb_op_angles* ops, int n_sweeps,
+                   const qb_sweep* sweeps, int n_passes, const qb_pass* passes, int n_pass_ops, const qb_pass_op* pass_ops,
+                   int64_t* plan_id) {
+    if (!ctx || !plan_id) return fail(QB_ERR_INVALID, "null argument");
+    if (n_qubits < 1 || n_qubits > 40) return fail(QB_ERR_INVALID, "n_qubits out of range");
+    if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
+    if (n_sweeps < 1 || n_passes < 1) return fail(QB_ERR_INVALID, "a plan needs at least one sweep with one pass");
+    const int n_eff = std::max(n_qubits, qb::kTileBits);
+    // validate the program: everything the kernel indexes with must be in range
+    for (int s = 0; s < n_sweeps; ++s) {
+        const qb_sweep& sw = sweeps[s];
+        if (sw.pass_begin < 0 || sw.pass_end > n_passes || sw.pass_end <= sw.pass_begin)
+            return fail(QB_ERR_INVALID, "sweep " + std::to_string(s) + ": bad pass range");
+        if (sw.pass_end - sw.pass_begin > qb::kMaxSweepPasses) return fail(QB_ERR_INVALID, "sweep has too many passes");
+        uint64_t mask = 0;
+        for (int i = 0; i < qb::kTileBits; ++i) {
+            const int q = sw.tile_qubits[i];
+            if (q < 0 || q >= n_eff || ((mask >> q) & 1)) return fail(QB_ERR_INVALID, "sweep " + std::to_string(s) + ": bad tile qubit");
+            if (i && q <= sw.tile_qubits[i - 1]) return fail(QB_ERR_INVALID, "tile qubits must ascend");
+            mask |= 1ull << q;
+        }
+        const int ob = passes[sw.pass_begin].op_begin, oe = passes[sw.pass_end - 1].op_end;
+        if (ob < 0 || oe > n_pass_ops || oe < ob || oe - ob > qb::kMaxSweepOps)
+            return fail(QB_ERR_INVALID, "sweep " + std::to_string(s) + ": bad op range / too many ops");
+        for (int p = sw.pass_begin; p < sw.pass_end; ++p) {
+            const qb_pass& ps = passes[p];
+            uint32_t used = 0;
+            for (int i = 0; i < qb::kRegBits; ++i) {
+                const int b = ps.reg_bits[i];
+                if (b < 0 || b >= qb::kTileBits || ((used >> b) & 1)) return fail(QB_ERR_INVALID, "bad register bit");
+                used |= 1u << b;
+            }
+            for (int i = 0; i < qb::kThreadBits; ++i) {
+                const int b = ps.thread_bits[i];
+                if (b >= qb::kTileBits || ((used >> b) & 1)) return fail(QB_ERR_INVALID, "bad thread bit");
+                used |= 1u << b;
+            }
+            if (p > sw.pass_begin && ps.op_begin != passes[p - 1].op_end) return fail(QB_ERR_INVALID, "pass op ranges must be contiguous");
+            for (int o = ps.op_begin; o < ps.op_end; ++o) {
+                const qb_pass_op& po = pass_ops[o];
+                if (po.op_index < 0 || po.op_index >= n_ops) return fail(QB_ERR_INVALID, "op index out of range");
+                if (po.kind == QB_OP_DENSE && (po.tgt_kind != QB_K_REG || po.tgt_pos >= qb::kRegBits))
+                    return fail(QB_ERR_INVALID, "dense op target must be a register bit");
+                auto bad = [&](int kind, int pos) {
+                    if (kind == QB_K_REG) return pos >= qb::kRegBits;
+                    if (kind == QB_K_THREAD) return pos >= qb::kTileBits;
+                    if (kind == QB_K_EXT) return pos >= 64;
+                    return kind != QB_K_NONE;
+                };
+                if (bad(po.tgt_kind, po.tgt_pos) || po.tgt_kind == QB_K_NONE || bad(po.ctrl_kind, po.ctrl_pos))
+                    return fail(QB_ERR_INVALID, "bad operand kind/position");
+            }
+        }
+    }
+    for (int o = 0; o < n_ops; ++o)
+        for (int j = 0; j < 4; ++j)
+            if (ops[o].slot[j] >= n_params) return fail(QB_ERR_INVALID, "angle slot out of range");
+
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    auto pl = std::make_unique<Plan>();
+    pl->n_qubits = n_qubits, pl->n_eff = n_eff, pl->dtype = dtype, pl->n_params = n_params, pl->n_ops = n_ops, pl->n_sweeps = n_sweeps;
+    QB_TRY(upload(ctx, pl->sweeps, sweeps, sizeof(qb_sweep) * size_t(n_sweeps)));
+    QB_TRY(upload(ctx, pl->passes, passes, sizeof(qb_pass) * size_t(n_passes)));
+    QB_TRY(upload(ctx, pl->pass_ops, pass_ops, sizeof(qb_pass_op) * size_t(n_pass_ops)));
+    QB_TRY(upload(ctx, pl->angles, ops, sizeof(qb_op_angles) * size_t(n_ops)));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *plan_id = ctx->next_id++;
+    ctx->plans[*plan_id] = std::move(pl);
+    return QB_OK;
+}
+
+int qb_plan_destroy(qb_context* ctx, int64_t plan_id) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    set_device(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    return ctx->plans.erase(plan_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown plan id");
+}
+
+// ---- Hamiltonians -------------------------------------------------------------------------------------
+int qb_hamiltonian_create(qb_context* ctx, int n_qubits, int n_terms, const uint64_t* x_masks, const uint64_t* z_masks,
+                          const double* coeff_re, const double* coeff_im, int build_table, int64_t* ham_id) {
+    if (!ctx || !ham_id) return fail(QB_ERR_INVALID, "null argument");
+    if (n_qubits < 1 || n_qubits > 40 || n_terms < 0) return fail(QB_ERR_INVALID, "bad Hamiltonian shape");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    auto ham = std::make_unique<Ham>();
+    ham->n_qubits = n_qubits;
+    // group by x mask, keeping first-appearance order; weights w = coeff * i^{#Y}
+    std::vector<uint64_t> xs;
+    std::vector<std::vector<int>> members;
+    for (int t = 0; t < n_terms; ++t) {
+        if ((x_masks[t] | z_masks[t]) >> n_qubits) return fail(QB_ERR_INVALID, "Pauli term acts outside the register");
+        size_t g = 0;
+        for (; g < xs.size(); ++g)
+            if (xs[g] == x_masks[t]) break;
+        if (g == xs.size()) xs.push_back(x_masks[t]), members.emplace_back();
+        members[g].push_back(t);
+    }
+    std::vector<uint64_t> dz;
+    std::vector<double> dc;
+    for (size_t g = 0; g < xs.size(); ++g) {
+        std::vector<uint64_t> z;
+        std::vector<double> wr, wi;
+        for (int t : members[g]) {
+            const int ny = __builtin_popcountll(x_masks[t] & z_masks[t]) & 3;
+            const double re = coeff_re[t], im = coeff_im ? coeff_im[t] : 0.0;
+            double r = re, i = im;  // multiply by i^ny
+            if (ny == 1) r = -im, i = re;
+            else if (ny == 2) r = -re, i = -im;
+            else if (ny == 3) r = im, i = -re;
+            z.push_back(z_masks[t]), wr.push_back(r), wi.push_back(i);
+            if (xs[g] == 0) dz.push_back(z_masks[t]), dc.push_back(re);
+        }
+        if (xs[g] != 0) ham->diagonal = false;
+        auto grp = std::make_unique<Group>();
+        grp->xmask = xs[g];
+        grp->n_terms = int(z.size());
+        QB_TRY(upload(ctx, grp->z, z.data(), sizeof(uint64_t) * z.size()));
+        QB_TRY(upload(ctx, grp->wr, wr.data(), sizeof(double) * wr.size()));
+        QB_TRY(upload(ctx, grp->wi, wi.data(), sizeof(double) * wi.size()));
+        QB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (xs[g] == 0) ham->groups.insert(ham->groups.begin(), std::move(grp));
+        else ham->groups.push_back(std::move(grp));
+    }
+    ham->n_diag = int(dz.size());
+    QB_TRY(upload(ctx, ham->diag_z, dz.data(), sizeof(uint64_t) * dz.size()));
+    QB_TRY(upload(ctx, ham->diag_c, dc.data(), sizeof(double) * dc.size()));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (build_table && ham->n_diag > 0) {
+        const int n_eff = std::max(n_qubits, qb::kTileBits);
+        const uint64_t size = uint64_t(1) << n_eff;
+        QB_TRY(ham->table.reserve(sizeof(double) * size));
+        ham->table_n_eff = n_eff;
+        const size_t smem = size_t(ham->n_diag) * (sizeof(uint64_t) + sizeof(double));
+        if (smem > 48 * 1024) return fail(QB_ERR_INVALID, "too many diagonal terms for the table builder");
+        const int blocks = int(std::min<uint64_t>(uint64_t(ctx->sm_count) * 8, std::max<uint64_t>(1, size / 256)));
+        qb::diag_table_kernel<<<blocks, 256, smem, ctx->stream>>>(ham->table.as<double>(), size, 0, ham->diag_z.as<uint64_t>(),
+                                                                  ham->diag_c.as<double>(), ham->n_diag);
+        QB_TRY(check_launch(ctx, "diag_table_kernel"));
+        QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *ham_id = ctx->next_id++;
+    ctx->hams[*ham_id] = std::move(ham);
+    return QB_OK;
+}
+
+int qb_hamiltonian_destroy(qb_context* ctx, int64_t ham_id) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    set_device(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    return ctx->hams.erase(ham_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
+}
+
+int qb_hamiltonian_diag_energies(qb_context* ctx, int64_t ham_id, int64_t n_states, const uint64_t* states, double* out_energies) {
+    if (!ctx || (n_states > 0 && (!states || !out_energies))) return fail(QB_ERR_INVALID, "null argument");
+    if (n_states <= 0) return QB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    Ham* ham = find_ham(ctx, ham_id);
+    if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
+    if (!ham->diagonal) return fail(QB_ERR_INVALID, "Hamiltonian has non-diagonal terms");
+    const size_t bytes = sizeof(uint64_t) * size_t(n_states);
+    QB_TRY(ctx->scratch.reserve(2 * bytes));
+    QB_CUDA(cudaEventSynchronize(ctx->pin_in_done));
+    QB_TRY(ctx->pin_in.reserve(bytes));
+    QB_TRY(ctx->pin_out.reserve(bytes));
+    std::memcpy(ctx->pin_in.p, states, bytes);
+    uint64_t* d_states = ctx->scratch.as<uint64_t>();
+    double* d_out = reinterpret_cast<double*>(d_states + n_states);
+    QB_CUDA(cudaMemcpyAsync(d_states, ctx->pin_in.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int blocks = int(std::min<int64_t>(1024, (n_states + 255) / 256));
+    qb::diag_lookup_kernel<<<blocks, 256, 0, ctx->stream>>>(d_states, n_states, ham->diag_z.as<uint64_t>(), ham->diag_c.as<double>(),
+                                                            ham->n_diag, d_out);
+    QB_TRY(check_launch(ctx, "diag_lookup_kernel"));
+    QB_CUDA(cudaMemcpyAsync(ctx->pin_out.p, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out_energies, ctx->pin_out.p, bytes);
+    return QB_OK;
+}
+
+// ---- resident batches -----------------------------------------------------------------------------------
+int qb_batch_create(qb_context* ctx, int batch, const int64_t* plan_ids, int64_t ham_id, int64_t* batch_id) {
+    if (!ctx || !plan_ids || !batch_id) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    Ham* ham = nullptr;
+    if (ham_id) {
+        ham = find_ham(ctx, ham_id);
+        if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
+    }
+    auto b = std::make_unique<DeviceBatch>();
+    QB_TRY(build_batch(ctx, *b, batch, plan_ids, ham, nullptr, 1, 0));
+    *batch_id = ctx->next_id++;
+    ctx->batches[*batch_id] = std::move(b);
+    return QB_OK;
+}
+
+static DeviceBatch* find_batch(qb_context* ctx, int64_t id) {
+    auto it = ctx->batches.find(id);
+    return it == ctx->batches.end() ? nullptr : it->second.get();
+}
+
+int qb_batch_set_params(qb_context* ctx, int64_t batch_id, const double* params, const int64_t* param_offsets) {
+    if (!ctx || !param_offsets) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    DeviceBatch* b = find_batch(ctx, batch_id);
+    if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
+    return batch_upload_params(ctx, *b, params, param_offsets);
+}
+
+int qb_batch_run(qb_context* ctx, int64_t batch_id) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    DeviceBatch* b = find_batch(ctx, batch_id);
+    if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
+    const int64_t before = ctx->launches;
+    QB_TRY(launch_circuits(ctx, *b));
+    if (b->ham) QB_TRY(launch_expectation(ctx, *b));
+    b->launches_per_run = ctx->launches - before;
+    return QB_OK;
+}
+
+int qb_batch_read(qb_context* ctx, int64_t batch_id, double* out_values) {
+    if (!ctx || !out_values) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    DeviceBatch* b = find_batch(ctx, batch_id);
+    if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
+    return batch_read(ctx, *b, out_values);
+}
+
+int qb_batch_destroy(qb_context* ctx, int64_t batch_id) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    set_device(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    return ctx->batches.erase(batch_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown batch id");
+}
+
+int qb_batch_stats(qb_context* ctx, int64_t batch_id, int64_t* n_sweep_launches, int64_t* n_state_sweeps, int64_t* sweep_bytes,
+                   int64_t* n_kernel_launches) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceBatch* b = find_batch(ctx, batch_id);
+    if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
+    if (n_sweep_launches) *n_sweep_launches = b->max_sweeps;
+    if (n_state_sweeps) *n_state_sweeps = b->n_state_sweeps;
+    if (sweep_bytes) *sweep_bytes = int64_t(2 * amp_bytes(b->dtype)) << b->n_eff;
+    if (n_kernel_launches) *n_kernel_launches = b->launches_per_run;
+    return QB_OK;
+}
+
+// ---- one-shot batched evaluation ---------------------------------------------------------------------
+int qb_evaluate_expectation(qb_context* ctx, int batch, const int64_t* plan_ids, const double* params, const int64_t* param_offsets,
+                            int64_t ham_id, double* out_values) {
+    if (!ctx || !plan_ids || !param_offsets || !out_values) return fail(QB_ERR_INVALID, "null argument");
+    if (batch <= 0) return QB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    Ham* ham = find_ham(ctx, ham_id);
+    if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
+    Plan* first = find_plan(ctx, plan_ids[0]);
+    if (!first) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[0]));
+    const int chunk = int(std::min<size_t>(size_t(batch), max_batch_for(ctx, first)));
+    for (int lo = 0; lo < batch; lo += chunk) {
+        const int n = std::min(chunk, batch - lo);
+        DeviceBatch& b = ctx->oneshot;
+        QB_TRY(build_batch(ctx, b, n, plan_ids + lo, ham, nullptr, 1, 0));
+        QB_TRY(batch_upload_params(ctx, b, params, param_offsets + lo));
+        QB_TRY(launch_circuits(ctx, b));
+        QB_TRY(launch_expectation(ctx, b));
+        QB_TRY(batch_read(ctx, b, out_values + lo));
+    }
+    return QB_OK;
+}
+
+int qb_sample(qb_context* ctx, int batch, const int64_t* plan_ids, const double* params, const int64_t* param_offsets, int shots,
+              const double* uniforms, int64_t* out_indices) {
+    if (!ctx || !plan_ids || !param_offsets || !uniforms || !out_indices) return fail(QB_ERR_INVALID, "null argument");
+    if (batch <= 0 || shots <= 0) return QB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    Plan* first = find_plan(ctx, plan_ids[0]);
+    if (!first) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[0]));
+    const int chunk = int(std::min<size_t>(size_t(batch), max_batch_for(ctx, first)));
+    for (int lo = 0; lo < batch; lo += chunk) {
+        const int n = std::min(chunk, batch - lo);
+        DeviceBatch& b = ctx->oneshot;
+        QB_TRY(build_batch(ctx, b, n, plan_ids + lo, nullptr, nullptr, 1, 0));
+        QB_TRY(batch_upload_params(ctx, b, params, param_offsets + lo));
+        QB_TRY(launch_circuits(ctx, b));
+        const uint64_t size = uint64_t(1) << b.n_eff;
+        const uint64_t n_chunks = size >> qb::kChunkBits;
+        const size_t u_bytes = sizeof(double) * size_t(n) * size_t(shots);
+        const size_t c_bytes = sizeof(double) * size_t(n) * n_chunks;
+        QB_TRY(ctx->scratch.reserve(2 * u_bytes + c_bytes));
+        double* d_uniforms = ctx->scratch.as<double>();
+        int64_t* d_indices = reinterpret_cast<int64_t*>(d_uniforms + size_t(n) * shots);
+        double* d_chunks = reinterpret_cast<double*>(d_indices + size_t(n) * shots);
+        QB_CUDA(cudaEventSynchronize(ctx->pin_in_done));
+        QB_TRY(ctx->pin_in.reserve(u_bytes));
+        QB_TRY(ctx->pin_out.reserve(u_bytes));
+        // uniforms in sorted (device) order
+        double* stage = static_cast<double*>(ctx->pin_in.p);
+        for (int pos = 0; pos < n; ++pos)
+            std::memcpy(stage + size_t(pos) * shots, uniforms + size_t(lo + b.order[pos]) * shots, sizeof(double) * size_t(shots));
+        QB_CUDA(cudaMemcpyAsync(d_uniforms, stage, u_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        dim3 cgrid(unsigned(std::min<uint64_t>((n_chunks + 7) / 8, 2048)), unsigned(n));
+        dim3 sgrid(unsigned((shots + 7) / 8), unsigned(n));
+        if (b.dtype == QB_C128) {
+            qb::chunk_prob_kernel<double><<<cgrid, 256, 0, ctx->stream>>>(b.states.as<double2>(), size, n_chunks, d_chunks);
+            QB_TRY(check_launch(ctx, "chunk_prob_kernel"));
+            qb::scan_chunks_kernel<<<n, 1024, 0, ctx->stream>>>(d_chunks, n_chunks);
+            QB_TRY(check_launch(ctx, "scan_chunks_kernel"));
+            qb::sample_kernel<double><<<sgrid, 256, 0, ctx->stream>>>(b.states.as<double2>(), size, d_chunks, n_chunks,
+                                                                       uint64_t(1) << b.n_qubits, d_uniforms, shots, d_indices);
+            QB_TRY(check_launch(ctx, "sample_kernel"));
+        } else {
+            qb::chunk_prob_kernel<float><<<cgrid, 256, 0, ctx->stream>>>(b.states.as<float2>(), size, n_chunks, d_chunks);
+            QB_TRY(check_launch(ctx, "chunk_prob_kernel"));
+            qb::scan_chunks_kernel<<<n, 1024, 0, ctx->stream>>>(d_chunks, n_chunks);
+            QB_TRY(check_launch(ctx, "scan_chunks_kernel"));
+            qb::sample_kernel<float><<<sgrid, 256, 0, ctx->stream>>>(b.states.as<float2>(), size, d_chunks, n_chunks,
+                                                                      uint64_t(1) << b.n_qubits, d_uniforms, shots, d_indices);
+            QB_TRY(check_launch(ctx, "sample_kernel"));
+        }
+        QB_CUDA(cudaMemcpyAsync(ctx->pin_out.p, d_indices, u_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        QB_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int64_t* sorted = static_cast<const int64_t*>(ctx->pin_out.p);
+        for (int pos = 0; pos < n; ++pos)
+            std::memcpy(out_indices + size_t(lo + b.order[pos]) * shots, sorted + size_t(pos) * shots, sizeof(int64_t) * size_t(shots));
+    }
+    return QB_OK;
+}
+
+int qb_statevector(qb_context* ctx, int64_t plan_id, const double* params, int n_params, double* out_re_im) {
+    if (!ctx || !out_re_im) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    Plan* pl = find_plan(ctx, plan_id);
+    if (!pl) return fail(QB_ERR_NOT_FOUND, "unknown plan id");
+    DeviceBatch& b = ctx->oneshot;
+    QB_TRY(build_batch(ctx, b, 1, &plan_id, nullptr, nullptr, 1, 0));
+    const int64_t offs[2] = {0, n_params};
+    QB_TRY(batch_upload_params(ctx, b, params, offs));
+    QB_TRY(launch_circuits(ctx, b));
+    const uint64_t size = uint64_t(1) << pl->n_qubits;
+    const void* src = b.states.p;
+    if (pl->dtype == QB_C64) {
+        QB_TRY(ctx->scratch.reserve(sizeof(double2) * size));
+        qb::to_c128_kernel<float><<<int(std::min<uint64_t>(1024, (size + 255) / 256)), 256, 0, ctx->stream>>>(b.states.as<float2>(),
+                                                                                                              ctx->scratch.as<double2>(), size);
+        QB_TRY(check_launch(ctx, "to_c128_kernel"));
+        src = ctx->scratch.p;
+    }
+    QB_CUDA(cudaMemcpyAsync(out_re_im, src, sizeof(double2) * size, cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QB_OK;
+}
+
+// ---- device-pointer entry points -----------------------------------------------------------------------
+int qb_apply_plan_device(qb_context* ctx, int64_t plan_id, const double* params_host, int n_params, void* d_state, int init_zero_state,
+                         uint64_t index_offset) {
+    if (!ctx || !d_state) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    DeviceBatch b;
+    QB_TRY(build_batch(ctx, b, 1, &plan_id, nullptr, d_state, init_zero_state, index_offset));
+    const int64_t offs[2] = {0, n_params};
+    QB_TRY(batch_upload_params(ctx, b, params_host, offs));
+    QB_TRY(launch_circuits(ctx, b));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QB_OK;
+}
+
+int qb_expectation_device(qb_context* ctx, int64_t ham_id, int dtype, int n_local, const void* d_state, uint64_t index_offset,
+                          double* out_value) {
+    if (!ctx || !d_state || !out_value) return fail(QB_ERR_INVALID, "null argument");
+    if (n_local < 8 || n_local > 36) return fail(QB_ERR_INVALID, "n_local out of range");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    Ham* ham = find_ham(ctx, ham_id);
+    if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
+    QB_TRY(ctx->scratch.reserve(sizeof(double) * 2048));
+    double* d_part = ctx->scratch.as<double>();
+    double* d_out = d_part + 1024;
+    if (dtype == QB_C128) QB_TRY(expectation_state_t<double>(ctx, *ham, d_state, n_local, index_offset, d_part, d_out));
+    else QB_TRY(expectation_state_t<float>(ctx, *ham, d_state, n_local, index_offset, d_part, d_out));
+    QB_CUDA(cudaMemcpyAsync(out_value, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QB_OK;
+}
+
+}  // extern "C"

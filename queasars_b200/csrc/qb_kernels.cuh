@@ -1,0 +1,525 @@
+// Hand-written sm_100a kernels of the EVQE circuit-evaluation hot path.
+//
+//   sweep_kernel        K1/K2  fused multi-gate application: one read + one write of the state per sweep,
+//                              gates applied in registers (2^4 amplitudes / thread), passes exchanged through
+//                              XOR-swizzled shared memory; optional fused diagonal-expectation epilogue (K3)
+//   bind_kernel                flat parameter vector -> 2x2 matrices, on the device
+//   diag_table_kernel   K3     E(k) = sum_t c_t (-1)^{popcount(k & z_t)}
+//   expect_table_kernel K3     sum_k |psi_k|^2 E(k)
+//   expect_group_kernel K4     Re sum_k psi_k conj(psi_{k^x}) W_x(k) for one x-mask group of a Pauli sum
+//   chunk_prob_kernel / scan_chunks_kernel / sample_kernel   K5  prefix-sum CDF sampling
+//
+// What the arithmetic follows ([upstream] = un-vendored qiskit 2.4.2, see oracle/qiskit_semantics.py):
+//   gate matrices   UGate / CU3Gate as emitted by evqe/quantum_circuit/quantum_gate.py:96-102, 157-165
+//   expectation     circuit_evaluation/circuit_evaluation.py:200-215 -> [upstream] Statevector.expectation_value
+//   sampling        circuit_evaluation/circuit_evaluation.py:29-59 -> [upstream] Statevector.sample_memory
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "queasars_b200.h"
+
+namespace qb {
+
+constexpr int kTileBits = QB_TILE_BITS;
+constexpr int kRegBits = QB_REG_BITS;
+constexpr int kThreadBits = kTileBits - kRegBits;
+constexpr int kThreads = 1 << kThreadBits;  // 256
+constexpr int kNReg = 1 << kRegBits;        // 16 amplitudes per thread
+constexpr int kTileSize = 1 << kTileBits;   // 4096 amplitudes per CTA
+constexpr int kMaxSweepOps = 112;
+constexpr int kMaxSweepPasses = 16;
+
+static_assert(kRegBits == 4, "register-pass code is written for 4 register bits");
+
+template <typename T> struct Cx;
+template <> struct Cx<double> { using type = double2; };
+template <> struct Cx<float> { using type = float2; };
+
+// One circuit evaluation inside a batched launch.
+struct BatchEntry {
+    const qb_sweep* sweeps;
+    const qb_pass* passes;
+    const qb_pass_op* pass_ops;
+    const qb_op_angles* angles;
+    const double* params;      // device, n_params
+    double* matrices;          // device, n_ops * 8 (bound 2x2 complex matrices, row-major re/im)
+    void* state;               // device, 2^n_eff amplitudes
+    const double* diag_table;  // device, 2^n_eff doubles, or nullptr
+    double* partials;          // device, one double per tile (fused expectation epilogue)
+    int32_t n_sweeps, n_ops, n_params, init_zero;
+    uint64_t index_offset;
+};
+
+template <typename T>
+constexpr size_t sweep_smem_bytes() {
+    return sizeof(typename Cx<T>::type) * kTileSize + sizeof(T) * 8 * kMaxSweepOps + sizeof(qb_pass_op) * kMaxSweepOps +
+           sizeof(qb_pass) * kMaxSweepPasses;
+}
+
+// XOR-fold of the tile-local index in groups of three bits: linear over GF(2), so
+// swz(a | b) == swz(a) ^ swz(b) for disjoint a, b.  Keeps 128-bit accesses of a quarter warp on eight
+// different 16-byte bank groups for every pass layout the planner emits (schedule.py:_thread_bit_order).
+__device__ __forceinline__ uint32_t swz(uint32_t e) { return e ^ (((e >> 3) ^ (e >> 6) ^ (e >> 9)) & 7u); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum (fixed tree): result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double total = 0.0;
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nw; ++w) total += s_red[w];
+    }
+    __syncthreads();
+    return total;
+}
+
+// Explicit global-space 128-bit / 64-bit accesses (the state pointer comes out of a struct in memory, which
+// the compiler would otherwise treat as a generic address).
+__device__ __forceinline__ double2 ld_state(const double2* p) {
+    double2 r;
+    asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ld_state(const float2* p) {
+    float2 r;
+    asm("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_state(double2* p, double2 v) {
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_state(float2* p, float2 v) {
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ double ld_table(const double* p) {
+    double r;
+    asm("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+template <typename T, int B>
+__device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[kNReg], const typename Cx<T>::type* __restrict__ m,
+                                            uint32_t cmask) {
+    using C = typename Cx<T>::type;
+    const C m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+#pragma unroll
+    for (int j = 0; j < kNReg; ++j) {
+        if (j & (1 << B)) continue;
+        if ((j & cmask) == cmask) {
+            const C x = a[j], y = a[j | (1 << B)];
+            C u, v;
+            u.x = m00.x * x.x - m00.y * x.y + m01.x * y.x - m01.y * y.y;
+            u.y = m00.x * x.y + m00.y * x.x + m01.x * y.y + m01.y * y.x;
+            v.x = m10.x * x.x - m10.y * x.y + m11.x * y.x - m11.y * y.y;
+            v.y = m10.x * x.y + m10.y * x.x + m11.x * y.y + m11.y * y.x;
+            a[j] = u;
+            a[j | (1 << B)] = v;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ typename Cx<T>::type cmul(typename Cx<T>::type a, typename Cx<T>::type b) {
+    typename Cx<T>::type r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sweep kernel: grid = (tiles, active batch entries), block = 256 threads, dynamic smem = sweep_smem_bytes<T>()
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation) {
+    using C = typename Cx<T>::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    C* tile = reinterpret_cast<C*>(smem);
+    C* s_mat = reinterpret_cast<C*>(smem + sizeof(C) * kTileSize);
+    qb_pass_op* s_ops = reinterpret_cast<qb_pass_op*>(smem + sizeof(C) * kTileSize + sizeof(T) * 8 * kMaxSweepOps);
+    qb_pass* s_pass = reinterpret_cast<qb_pass*>(reinterpret_cast<unsigned char*>(s_ops) + sizeof(qb_pass_op) * kMaxSweepOps);
+    __shared__ qb_sweep s_sweep;
+    __shared__ double s_red[kThreads / 32];
+
+    const BatchEntry en = entries[blockIdx.y];  // block-uniform copy into registers
+    if (sweep_idx >= en.n_sweeps) return;
+    const int tid = threadIdx.x;
+
+    if (tid < int(sizeof(qb_sweep) / 4))
+        reinterpret_cast<int32_t*>(&s_sweep)[tid] = reinterpret_cast<const int32_t*>(en.sweeps + sweep_idx)[tid];
+    __syncthreads();
+    const int pass_begin = s_sweep.pass_begin;
+    const int n_pass = s_sweep.pass_end - pass_begin;
+    for (int i = tid; i < n_pass * int(sizeof(qb_pass) / 4); i += kThreads)
+        reinterpret_cast<int32_t*>(s_pass)[i] = reinterpret_cast<const int32_t*>(en.passes + pass_begin)[i];
+    __syncthreads();
+    const int op_begin = s_pass[0].op_begin;
+    const int n_sop = s_pass[n_pass - 1].op_end - op_begin;
+    for (int i = tid; i < n_sop * int(sizeof(qb_pass_op) / 4); i += kThreads)
+        reinterpret_cast<int32_t*>(s_ops)[i] = reinterpret_cast<const int32_t*>(en.pass_ops + op_begin)[i];
+    __syncthreads();
+    {
+        T* s_mat_t = reinterpret_cast<T*>(s_mat);
+        const double* __restrict__ mats = en.matrices;
+        for (int i = tid; i < n_sop * 8; i += kThreads)
+            s_mat_t[i] = static_cast<T>(mats[size_t(s_ops[i >> 3].op_index) * 8 + (i & 7)]);
+    }
+
+    // tile base index: scatter blockIdx.x over the qubits that are not tile bits
+    uint64_t tile_mask = 0;
+#pragma unroll
+    for (int i = 0; i < kTileBits; ++i) tile_mask |= 1ull << s_sweep.tile_qubits[i];
+    uint64_t base = 0;
+    {
+        uint64_t t = blockIdx.x;
+        for (int q = 0; q < n_eff; ++q)
+            if (!((tile_mask >> q) & 1ull)) {
+                base |= (t & 1ull) << q;
+                t >>= 1;
+            }
+    }
+    const uint64_t gbase = base | en.index_offset;
+    C* __restrict__ st = reinterpret_cast<C*>(en.state);
+    const bool do_expect = fuse_expectation && (sweep_idx == en.n_sweeps - 1) && (en.diag_table != nullptr);
+    const double* __restrict__ table = en.diag_table;
+
+    C a[kNReg];
+    for (int p = 0; p < n_pass; ++p) {
+        const qb_pass& ps = s_pass[p];
+        const bool first = (p == 0), last = (p == n_pass - 1);
+        // thread part of the tile-local index and the global offset it maps to
+        uint32_t e_thr = 0;
+        uint64_t g_thr = 0;
+#pragma unroll
+        for (int b = 0; b < kThreadBits; ++b) {
+            const uint32_t bit = (tid >> b) & 1u;
+            const int pos = ps.thread_bits[b];
+            e_thr |= bit << pos;
+            g_thr |= uint64_t(bit) << s_sweep.tile_qubits[pos];
+        }
+        const uint32_t s_thr = swz(e_thr);
+        uint32_t so[kRegBits];
+        uint64_t go[kRegBits];
+#pragma unroll
+        for (int i = 0; i < kRegBits; ++i) {
+            so[i] = swz(1u << ps.reg_bits[i]);
+            go[i] = 1ull << s_sweep.tile_qubits[ps.reg_bits[i]];
+        }
+        const uint64_t g0 = base | g_thr;
+
+        // ---- load ----
+        if (first) {
+            if (sweep_idx == 0 && en.init_zero) {
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j) {
+                    const uint64_t idx = g0 | ((j & 1) ? go[0] : 0) | ((j & 2) ? go[1] : 0) | ((j & 4) ? go[2] : 0) | ((j & 8) ? go[3] : 0);
+                    a[j].x = ((idx | en.index_offset) == 0) ? T(1) : T(0);
+                    a[j].y = T(0);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j) {
+                    const uint64_t idx = g0 | ((j & 1) ? go[0] : 0) | ((j & 2) ? go[1] : 0) | ((j & 4) ? go[2] : 0) | ((j & 8) ? go[3] : 0);
+                    a[j] = ld_state(st + idx);
+                }
+            }
+            __syncthreads();  // staged matrices / ops visible before the first compute
+        } else {
+#pragma unroll
+            for (int j = 0; j < kNReg; ++j) {
+                const uint32_t si = s_thr ^ ((j & 1) ? so[0] : 0) ^ ((j & 2) ? so[1] : 0) ^ ((j & 4) ? so[2] : 0) ^ ((j & 8) ? so[3] : 0);
+                a[j] = tile[si];
+            }
+        }
+
+        // ---- gates of this pass, applied in registers ----
+        for (int o = ps.op_begin - op_begin; o < ps.op_end - op_begin; ++o) {
+            const qb_pass_op po = s_ops[o];
+            const C* m = s_mat + o * 4;
+            bool act = true;
+            uint32_t cmask = 0;
+            if (po.ctrl_kind == QB_K_REG) cmask = 1u << po.ctrl_pos;
+            else if (po.ctrl_kind == QB_K_THREAD) act = (e_thr >> po.ctrl_pos) & 1u;
+            else if (po.ctrl_kind == QB_K_EXT) act = (gbase >> po.ctrl_pos) & 1ull;
+            if (!act) continue;
+            if (po.kind == QB_OP_DENSE) {
+                switch (po.tgt_pos) {
+                    case 0: apply_dense<T, 0>(a, m, cmask); break;
+                    case 1: apply_dense<T, 1>(a, m, cmask); break;
+                    case 2: apply_dense<T, 2>(a, m, cmask); break;
+                    default: apply_dense<T, 3>(a, m, cmask); break;
+                }
+            } else {
+                const C d0 = m[0], d1 = m[3];
+                if (po.tgt_kind == QB_K_REG) {
+                    const uint32_t tb = 1u << po.tgt_pos;
+#pragma unroll
+                    for (int j = 0; j < kNReg; ++j)
+                        if ((j & cmask) == cmask) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
+                } else {
+                    const bool one = (po.tgt_kind == QB_K_THREAD) ? ((e_thr >> po.tgt_pos) & 1u) : ((gbase >> po.tgt_pos) & 1ull);
+                    const C d = one ? d1 : d0;
+#pragma unroll
+                    for (int j = 0; j < kNReg; ++j)
+                        if ((j & cmask) == cmask) a[j] = cmul<T>(a[j], d);
+                }
+            }
+        }
+
+        // ---- store ----
+        if (last) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < kNReg; ++j) {
+                const uint64_t idx = g0 | ((j & 1) ? go[0] : 0) | ((j & 2) ? go[1] : 0) | ((j & 4) ? go[2] : 0) | ((j & 8) ? go[3] : 0);
+                st_state(st + idx, a[j]);
+                if (do_expect) acc += (double(a[j].x) * double(a[j].x) + double(a[j].y) * double(a[j].y)) * ld_table(table + idx);
+            }
+            if (do_expect) {
+                const double total = block_sum(acc, s_red);
+                if (tid == 0) en.partials[blockIdx.x] = total;
+            }
+        } else {
+            if (!first) __syncthreads();  // everyone finished reading the previous layout
+#pragma unroll
+            for (int j = 0; j < kNReg; ++j) {
+                const uint32_t si = s_thr ^ ((j & 1) ? so[0] : 0) ^ ((j & 2) ? so[1] : 0) ^ ((j & 4) ? so[2] : 0) ^ ((j & 8) ? so[3] : 0);
+                tile[si] = a[j];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parameter binding: grid = batch entries
+// ---------------------------------------------------------------------------------------------------
+__global__ void bind_kernel(const BatchEntry* __restrict__ entries) {
+    const BatchEntry& en = entries[blockIdx.x];
+    for (int o = threadIdx.x; o < en.n_ops; o += blockDim.x) {
+        const qb_op_angles& ang = en.angles[o];
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = ang.cnst[j] + (ang.slot[j] >= 0 ? ang.coeff[j] * en.params[ang.slot[j]] : 0.0);
+        const double g = v[0], t = v[1], p = v[2], l = v[3];
+        double* m = en.matrices + size_t(o) * 8;
+        double s, c;
+        if (ang.kind == QB_OP_DIAG) {
+            sincos(g, &s, &c);
+            m[0] = c, m[1] = s, m[2] = 0.0, m[3] = 0.0, m[4] = 0.0, m[5] = 0.0;
+            sincos(g + l, &s, &c);
+            m[6] = c, m[7] = s;
+        } else {
+            double sh, ch;
+            sincos(0.5 * t, &sh, &ch);
+            sincos(g, &s, &c);
+            m[0] = c * ch, m[1] = s * ch;
+            sincos(g + l, &s, &c);
+            m[2] = -c * sh, m[3] = -s * sh;
+            sincos(g + p, &s, &c);
+            m[4] = c * sh, m[5] = s * sh;
+            sincos(g + p + l, &s, &c);
+            m[6] = c * ch, m[7] = s * ch;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// diagonal energies
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double diag_energy(uint64_t k, const uint64_t* __restrict__ z, const double* __restrict__ c, int n_terms) {
+    double e = 0.0;
+    for (int t = 0; t < n_terms; ++t) e += (__popcll(k & z[t]) & 1) ? -c[t] : c[t];
+    return e;
+}
+
+__global__ void diag_table_kernel(double* __restrict__ table, uint64_t size, uint64_t index_offset,
+                                  const uint64_t* __restrict__ z, const double* __restrict__ c, int n_terms) {
+    extern __shared__ unsigned char dsm[];
+    uint64_t* sz = reinterpret_cast<uint64_t*>(dsm);
+    double* sc = reinterpret_cast<double*>(sz + n_terms);
+    for (int t = threadIdx.x; t < n_terms; t += blockDim.x) sz[t] = z[t], sc[t] = c[t];
+    __syncthreads();
+    for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x)
+        table[k] = diag_energy(k | index_offset, sz, sc, n_terms);
+}
+
+__global__ void diag_lookup_kernel(const uint64_t* __restrict__ states, int64_t n_states, const uint64_t* __restrict__ z,
+                                   const double* __restrict__ c, int n_terms, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n_states; i += int64_t(gridDim.x) * blockDim.x)
+        out[i] = diag_energy(states[i], z, c, n_terms);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+expect_table_kernel(const typename Cx<T>::type* __restrict__ state, const double* __restrict__ table, uint64_t size,
+                    double* __restrict__ partials) {
+    __shared__ double s_red[8];
+    double acc = 0.0;
+    for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x) {
+        const auto a = state[k];
+        acc += (double(a.x) * double(a.x) + double(a.y) * double(a.y)) * table[k];
+    }
+    const double total = block_sum(acc, s_red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+// One x-mask group of a Pauli sum:  sum_k Re[ psi_k conj(psi_{k^x}) W(k) ],  W(k) = sum_t w_t (-1)^{pc(k & z_t)},
+// w_t = coeff_t * i^{#Y_t}.  x == 0 is the diagonal group evaluated on the fly.
+template <typename T>
+__global__ void __launch_bounds__(256)
+expect_group_kernel(const typename Cx<T>::type* __restrict__ state, uint64_t size, uint64_t index_offset, uint64_t xmask,
+                    const uint64_t* __restrict__ z, const double* __restrict__ wr, const double* __restrict__ wi, int n_terms,
+                    double* __restrict__ partials) {
+    extern __shared__ unsigned char dsm[];
+    uint64_t* sz = reinterpret_cast<uint64_t*>(dsm);
+    double* swr = reinterpret_cast<double*>(sz + n_terms);
+    double* swi = swr + n_terms;
+    __shared__ double s_red[8];
+    for (int t = threadIdx.x; t < n_terms; t += blockDim.x) sz[t] = z[t], swr[t] = wr[t], swi[t] = wi[t];
+    __syncthreads();
+    double acc = 0.0;
+    for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x) {
+        const auto a = state[k];
+        const auto b = xmask ? state[k ^ xmask] : a;
+        const double pr = double(a.x) * double(b.x) + double(a.y) * double(b.y);
+        const double pi = double(a.y) * double(b.x) - double(a.x) * double(b.y);
+        double Wr = 0.0, Wi = 0.0;
+        const uint64_t kk = k | index_offset;
+        for (int t = 0; t < n_terms; ++t) {
+            const bool neg = __popcll(kk & sz[t]) & 1;
+            Wr += neg ? -swr[t] : swr[t];
+            Wi += neg ? -swi[t] : swi[t];
+        }
+        acc += pr * Wr - pi * Wi;
+    }
+    const double total = block_sum(acc, s_red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+// out[b] (+)= sum_i partials[b * stride + i]  in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const double* __restrict__ partials, int64_t stride, int64_t count, double* __restrict__ out, int accumulate) {
+    __shared__ double s_red[8];
+    const double* p = partials + blockIdx.x * stride;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) acc += p[i];
+    const double total = block_sum(acc, s_red);
+    if (threadIdx.x == 0) out[blockIdx.x] = accumulate ? out[blockIdx.x] + total : total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sampling: |psi|^2 chunk sums -> inclusive scan of chunk sums -> per-shot two-level search
+// ---------------------------------------------------------------------------------------------------
+constexpr int kChunkBits = 9;  // 512 amplitudes per chunk
+constexpr int kChunk = 1 << kChunkBits;
+
+// grid.x covers chunks (one warp per chunk), grid.y = batch entry; states are `state_stride` amplitudes apart
+template <typename T>
+__global__ void __launch_bounds__(256)
+chunk_prob_kernel(const typename Cx<T>::type* __restrict__ states, uint64_t state_stride, uint64_t n_chunks,
+                  double* __restrict__ chunk_sums) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_per_grid = uint64_t(gridDim.x) * (blockDim.x >> 5);
+    const auto* st = states + blockIdx.y * state_stride;
+    double* out = chunk_sums + blockIdx.y * n_chunks;
+    for (uint64_t ch = blockIdx.x * uint64_t(blockDim.x >> 5) + (threadIdx.x >> 5); ch < n_chunks; ch += warps_per_grid) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < kChunk / 32; ++i) {
+            const auto a = st[ch * kChunk + i * 32 + lane];
+            acc += double(a.x) * double(a.x) + double(a.y) * double(a.y);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[ch] = acc;
+    }
+}
+
+// in-place inclusive scan of n_chunks doubles per batch entry; one CTA of 1024 threads per entry
+__global__ void __launch_bounds__(1024)
+scan_chunks_kernel(double* __restrict__ chunk_sums, uint64_t n_chunks) {
+    __shared__ double s_tot[1024];
+    double* data = chunk_sums + blockIdx.x * n_chunks;
+    const uint64_t per = (n_chunks + blockDim.x - 1) / blockDim.x;
+    const uint64_t lo = threadIdx.x * per, hi = (lo + per < n_chunks) ? lo + per : n_chunks;
+    double acc = 0.0;
+    for (uint64_t i = lo; i < hi; ++i) acc += data[i];
+    s_tot[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = 0.0;
+        for (int i = 0; i < int(blockDim.x); ++i) {
+            const double v = s_tot[i];
+            s_tot[i] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    double run = s_tot[threadIdx.x];
+    for (uint64_t i = lo; i < hi; ++i) {
+        run += data[i];
+        data[i] = run;
+    }
+}
+
+// one warp per shot: index = first k with cdf(k) / total > u   (searchsorted(cdf / cdf[-1], u, side='right'))
+template <typename T>
+__global__ void __launch_bounds__(256)
+sample_kernel(const typename Cx<T>::type* __restrict__ states, uint64_t state_stride, const double* __restrict__ chunk_cdf,
+              uint64_t n_chunks, uint64_t valid_size, const double* __restrict__ uniforms, int shots, int64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int shot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (shot >= shots) return;
+    const auto* st = states + blockIdx.y * state_stride;
+    const double* cdf = chunk_cdf + blockIdx.y * n_chunks;
+    const double total = cdf[n_chunks - 1];
+    const double u = uniforms[blockIdx.y * uint64_t(shots) + shot];
+    // first chunk whose inclusive cdf / total exceeds u
+    uint64_t lo = 0, hi = n_chunks - 1;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (cdf[mid] / total > u) hi = mid;
+        else lo = mid + 1;
+    }
+    double run = lo ? cdf[lo - 1] : 0.0;
+    int64_t found = -1;
+    for (int i = 0; i < kChunk / 32 && found < 0; ++i) {
+        const uint64_t k = lo * kChunk + i * 32 + lane;
+        const auto a = st[k];
+        const double pr = double(a.x) * double(a.x) + double(a.y) * double(a.y);
+        double inc = pr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double nb = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nb;
+        }
+        const bool hit = ((run + inc) / total > u);
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (ballot) found = int64_t(lo * kChunk + i * 32 + (__ffs(ballot) - 1));
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (found < 0) found = int64_t(lo * kChunk + kChunk - 1);  // rounding at the very top of a chunk
+    if (uint64_t(found) >= valid_size) found = int64_t(valid_size - 1);
+    if (lane == 0) out[blockIdx.y * uint64_t(shots) + shot] = found;
+}
+
+template <typename T>
+__global__ void to_c128_kernel(const typename Cx<T>::type* __restrict__ src, double2* __restrict__ dst, uint64_t size) {
+    for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x) {
+        const auto a = src[k];
+        dst[k] = make_double2(double(a.x), double(a.y));
+    }
+}
+
+}  // namespace qb

@@ -1,0 +1,265 @@
+"""Python face of the native engine: compiles gate lists into device plans, uploads Hamiltonians and
+submits *batches* of (plan, parameter vector) evaluations through the C-ABI.
+
+This is the "batched submission of each generation's circuits" named by the north star: where the
+reference funnels concurrent threads' pubs through ``BatchingMutexPrimitiveJobRunner`` with a fixed 0.1 s
+sleep (/root/reference/queasars/circuit_evaluation/mutex_primitives.py:67-199), one ``Engine.expectation``
+/ ``Engine.sample`` call evaluates the whole list in one native call; ``queasars_b200.batching`` adds the
+cross-thread coalescing on top.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+import weakref
+from ctypes import byref, c_double, c_int64, c_void_p
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native, schedule
+from .gate_list import GateList
+
+_DTYPES = {"complex128": _native.QB_C128, "c128": _native.QB_C128, "complex64": _native.QB_C64, "c64": _native.QB_C64}
+
+
+def _dtype_code(dtype) -> int:
+    key = np.dtype(dtype).name if not isinstance(dtype, str) else dtype
+    if key not in _DTYPES:
+        raise ValueError(f"dtype must be complex128 or complex64, got {dtype!r}")
+    return _DTYPES[key]
+
+
+class PlanHandle:
+    __slots__ = ("plan_id", "n_qubits", "n_params", "n_ops", "n_sweeps", "n_passes", "dtype", "__weakref__")
+
+    def __init__(self, plan_id, n_qubits, n_params, n_ops, n_sweeps, n_passes, dtype):
+        self.plan_id, self.n_qubits, self.n_params = plan_id, n_qubits, n_params
+        self.n_ops, self.n_sweeps, self.n_passes, self.dtype = n_ops, n_sweeps, n_passes, dtype
+
+
+class HamiltonianHandle:
+    __slots__ = ("ham_id", "n_qubits", "diagonal", "z_masks", "coeffs", "n_terms", "__weakref__")
+
+    def __init__(self, ham_id, n_qubits, diagonal, z_masks, coeffs, n_terms):
+        self.ham_id, self.n_qubits, self.diagonal = ham_id, n_qubits, diagonal
+        self.z_masks, self.coeffs, self.n_terms = z_masks, coeffs, n_terms
+
+
+def operator_terms(operator):
+    """``SparsePauliOp``-like -> (n_qubits, x_masks, z_masks, coeffs) via the Qiskit API ``to_list()``
+    (labels little-endian, right-most char = qubit 0)."""
+    if hasattr(operator, "masks") and hasattr(operator, "num_qubits"):
+        x, z, c = operator.masks()
+        return int(operator.num_qubits), x, z, c
+    if not hasattr(operator, "to_list"):
+        raise TypeError(f"cannot extract Pauli terms from {type(operator).__name__}; a SparsePauliOp is required")
+    from .operators import SparsePauliOp
+
+    items = operator.to_list()
+    op = SparsePauliOp.from_list(items, num_qubits=int(operator.num_qubits))
+    x, z, c = op.masks()
+    return op.num_qubits, x, z, c
+
+
+class Engine:
+    """One native context (one CUDA device, one stream).  Thread-safe."""
+
+    def __init__(self, device: int = 0, dtype="complex128", stream: Optional[int] = None, workspace_limit: int = 0):
+        self._lib = _native.load()
+        self.device = int(device)
+        self.dtype = "complex128" if _dtype_code(dtype) == _native.QB_C128 else "complex64"
+        self._dtype_code = _dtype_code(dtype)
+        handle = c_void_p()
+        _native.check(self._lib.qb_context_create(self.device, c_void_p(stream) if stream else None, byref(handle)))
+        self._ctx = handle
+        self._lock = threading.Lock()
+        self._plan_cache: dict = {}
+        self._finalizer = weakref.finalize(self, Engine._destroy, self._lib, handle)
+        if workspace_limit:
+            _native.check(self._lib.qb_context_set_workspace_limit(self._ctx, int(workspace_limit)))
+
+    @staticmethod
+    def _destroy(lib, handle):
+        lib.qb_context_destroy(handle)
+
+    def close(self):
+        self._finalizer()
+
+    # ------------------------------------------------------------------ introspection
+    @property
+    def stream(self) -> int:
+        return int(self._lib.qb_context_stream(self._ctx) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.qb_context_launch_count(self._ctx))
+
+    def synchronize(self):
+        _native.check(self._lib.qb_context_synchronize(self._ctx))
+
+    # ------------------------------------------------------------------ compilation
+    def compile(self, gates: GateList, dtype=None) -> PlanHandle:
+        code = self._dtype_code if dtype is None else _dtype_code(dtype)
+        key = (code, gates.structure_key())
+        with self._lock:
+            hit = self._plan_cache.get(key)
+        if hit is not None:
+            return hit
+        plan = schedule.plan_circuit(gates.ops, gates.n_qubits)
+        sweeps, passes, pass_ops, angles = schedule.encode_plan(plan, gates.ops)
+        n_pass_ops = sum(s.n_ops for s in plan.sweeps)
+        plan_id = c_int64()
+        _native.check(
+            self._lib.qb_plan_create(
+                self._ctx, gates.n_qubits, code, gates.n_params, len(gates.ops), _native.ptr(angles), len(sweeps), _native.ptr(sweeps),
+                len(passes), _native.ptr(passes), n_pass_ops, _native.ptr(pass_ops), byref(plan_id),
+            )
+        )
+        handle = PlanHandle(plan_id.value, gates.n_qubits, gates.n_params, len(gates.ops), len(sweeps), len(passes), code)
+        weakref.finalize(handle, self._release_plan, self._lib, self._ctx, plan_id.value, self._finalizer)
+        with self._lock:
+            if len(self._plan_cache) > 4096:
+                self._plan_cache.clear()
+            self._plan_cache[key] = handle
+        return handle
+
+    @staticmethod
+    def _release_plan(lib, ctx, plan_id, engine_finalizer):
+        if engine_finalizer.alive:
+            lib.qb_plan_destroy(ctx, plan_id)
+
+    def hamiltonian(self, operator, build_table: Optional[bool] = None) -> HamiltonianHandle:
+        n, x, z, c = operator_terms(operator)
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        cre = np.ascontiguousarray(c.real, dtype=np.float64)
+        cim = np.ascontiguousarray(c.imag, dtype=np.float64)
+        diagonal = not bool(np.any(x))
+        n_diag = int(np.count_nonzero(x == 0))
+        if build_table is None:
+            # a table costs 8 B * 2^n once and turns the per-amplitude cost from O(terms) into one load
+            build_table = n_diag > 8 and n <= 32
+        ham_id = c_int64()
+        _native.check(
+            self._lib.qb_hamiltonian_create(self._ctx, n, len(cre), _native.ptr(x), _native.ptr(z), _native.ptr(cre), _native.ptr(cim), int(bool(build_table)), byref(ham_id))
+        )
+        handle = HamiltonianHandle(ham_id.value, n, diagonal, z[x == 0].copy(), cre[x == 0].copy(), len(cre))
+        weakref.finalize(handle, self._release_ham, self._lib, self._ctx, ham_id.value, self._finalizer)
+        return handle
+
+    @staticmethod
+    def _release_ham(lib, ctx, ham_id, engine_finalizer):
+        if engine_finalizer.alive:
+            lib.qb_hamiltonian_destroy(ctx, ham_id)
+
+    # ------------------------------------------------------------------ batched evaluation
+    @staticmethod
+    def _pack(plans: Sequence[PlanHandle], params: Sequence[Sequence[float]]):
+        if len(plans) != len(params):
+            raise ValueError(f"{len(plans)} circuits but {len(params)} parameter vectors")
+        ids = np.fromiter((p.plan_id for p in plans), dtype=np.int64, count=len(plans))
+        offsets = np.zeros(len(plans) + 1, dtype=np.int64)
+        chunks = []
+        for i, (pl, vals) in enumerate(zip(plans, params)):
+            arr = np.asarray(vals, dtype=np.float64).reshape(-1)
+            if arr.size != pl.n_params:
+                raise ValueError(f"circuit {i} has {pl.n_params} parameters but {arr.size} values were given")
+            chunks.append(arr)
+            offsets[i + 1] = offsets[i] + arr.size
+        flat = np.concatenate(chunks) if chunks and offsets[-1] else np.zeros(1, dtype=np.float64)
+        return ids, np.ascontiguousarray(flat), offsets
+
+    def expectation(self, plans: Sequence[PlanHandle], params: Sequence[Sequence[float]], ham: HamiltonianHandle) -> np.ndarray:
+        if not plans:
+            return np.zeros(0)
+        ids, flat, offsets = self._pack(plans, params)
+        out = np.empty(len(plans), dtype=np.float64)
+        _native.check(self._lib.qb_evaluate_expectation(self._ctx, len(plans), _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), ham.ham_id, _native.ptr(out)))
+        return out
+
+    def sample(self, plans: Sequence[PlanHandle], params: Sequence[Sequence[float]], shots: int, uniforms: np.ndarray) -> np.ndarray:
+        if not plans:
+            return np.zeros((0, shots), dtype=np.int64)
+        ids, flat, offsets = self._pack(plans, params)
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(len(plans), shots)
+        out = np.empty((len(plans), shots), dtype=np.int64)
+        _native.check(self._lib.qb_sample(self._ctx, len(plans), _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), int(shots), _native.ptr(uniforms), _native.ptr(out)))
+        return out
+
+    def statevector(self, plan: PlanHandle, params: Sequence[float]) -> np.ndarray:
+        vals = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
+        if vals.size != plan.n_params:
+            raise ValueError(f"circuit has {plan.n_params} parameters but {vals.size} values were given")
+        out = np.empty(1 << plan.n_qubits, dtype=np.complex128)
+        buf = vals if vals.size else np.zeros(1)
+        _native.check(self._lib.qb_statevector(self._ctx, plan.plan_id, _native.ptr(buf), int(vals.size), _native.ptr(out)))
+        return out
+
+    def diag_energies(self, ham: HamiltonianHandle, states: np.ndarray) -> np.ndarray:
+        states = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1)
+        out = np.empty(states.size, dtype=np.float64)
+        if states.size:
+            _native.check(self._lib.qb_hamiltonian_diag_energies(self._ctx, ham.ham_id, states.size, _native.ptr(states), _native.ptr(out)))
+        return out
+
+    def resident_batch(self, plans: Sequence[PlanHandle], ham: Optional[HamiltonianHandle]) -> "ResidentBatch":
+        return ResidentBatch(self, plans, ham)
+
+    # ------------------------------------------------------------------ device-pointer entry points
+    def apply_plan_device(self, plan: PlanHandle, params: Sequence[float], state_ptr: int, init_zero_state: bool, index_offset: int = 0):
+        vals = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
+        buf = vals if vals.size else np.zeros(1)
+        _native.check(self._lib.qb_apply_plan_device(self._ctx, plan.plan_id, _native.ptr(buf), int(vals.size), c_void_p(state_ptr), int(init_zero_state), int(index_offset)))
+
+    def expectation_device(self, ham: HamiltonianHandle, dtype, n_local: int, state_ptr: int, index_offset: int = 0) -> float:
+        out = c_double()
+        _native.check(self._lib.qb_expectation_device(self._ctx, ham.ham_id, _dtype_code(dtype), int(n_local), c_void_p(state_ptr), int(index_offset), byref(out)))
+        return out.value
+
+
+class ResidentBatch:
+    """A fixed list of circuits whose device buffers stay allocated: ``set_params`` (H2D), ``run`` (kernels
+    only, asynchronous), ``read`` (D2H + sync).  Used by bench.py and by optimizer inner loops."""
+
+    def __init__(self, engine: Engine, plans: Sequence[PlanHandle], ham: Optional[HamiltonianHandle]):
+        self._engine = engine
+        self._plans = list(plans)
+        self._ham = ham
+        ids = np.fromiter((p.plan_id for p in self._plans), dtype=np.int64, count=len(self._plans))
+        batch_id = c_int64()
+        _native.check(engine._lib.qb_batch_create(engine._ctx, len(self._plans), _native.ptr(ids), ham.ham_id if ham else 0, byref(batch_id)))
+        self.batch_id = batch_id.value
+        self._finalizer = weakref.finalize(self, ResidentBatch._destroy, engine._lib, engine._ctx, self.batch_id, engine._finalizer)
+
+    @staticmethod
+    def _destroy(lib, ctx, batch_id, engine_finalizer):
+        if engine_finalizer.alive:
+            lib.qb_batch_destroy(ctx, batch_id)
+
+    def __len__(self):
+        return len(self._plans)
+
+    def set_params(self, params: Sequence[Sequence[float]]):
+        _, flat, offsets = Engine._pack(self._plans, params)
+        _native.check(self._engine._lib.qb_batch_set_params(self._engine._ctx, self.batch_id, _native.ptr(flat), _native.ptr(offsets)))
+        return int(flat.nbytes if offsets[-1] else 0)
+
+    def set_params_flat(self, flat: np.ndarray, offsets: np.ndarray):
+        _native.check(self._engine._lib.qb_batch_set_params(self._engine._ctx, self.batch_id, _native.ptr(flat), _native.ptr(offsets)))
+
+    def run(self):
+        _native.check(self._engine._lib.qb_batch_run(self._engine._ctx, self.batch_id))
+
+    def read(self) -> np.ndarray:
+        out = np.empty(len(self._plans), dtype=np.float64)
+        _native.check(self._engine._lib.qb_batch_read(self._engine._ctx, self.batch_id, _native.ptr(out)))
+        return out
+
+    def stats(self) -> dict:
+        a, b, c, d = c_int64(), c_int64(), c_int64(), c_int64()
+        _native.check(self._engine._lib.qb_batch_stats(self._engine._ctx, self.batch_id, byref(a), byref(b), byref(c), byref(d)))
+        return {"sweep_launches": a.value, "state_sweeps": b.value, "sweep_bytes": c.value, "kernel_launches": d.value}
+
+    def close(self):
+        self._finalizer()

@@ -1,0 +1,209 @@
+"""B200 circuit evaluators: drop-ins for the three evaluator classes of
+/root/reference/queasars/circuit_evaluation/circuit_evaluation.py behind the same interface
+
+    evaluate_circuits(circuits: list[QuantumCircuit], parameter_values: list[list[float]]) -> list[float]
+    n_qubits -> int                                                        (circuit_evaluation.py:62-87)
+
+with the same constructor argument order, the same ``ValueError`` conditions (alpha outside (0, 1],
+non-SparsePauliOp operator on the sampler route, qubit-count mismatch of ``initial_state_circuit``) and the same
+result semantics, but evaluating the whole list in one batched GPU submission instead of one primitive pub
+per circuit.  Inputs are never mutated; outputs are fresh Python floats.
+
+Differences that are deliberate and documented in DESIGN.md:
+  * the first constructor argument must be a ``B200EstimatorV2`` / ``B200SamplerV2`` (it carries device,
+    dtype and seed); any other primitive type raises ``TypeError`` -- to drive a foreign primitive use the
+    reference's own evaluators, to drive the B200 engine through the reference's own evaluators hand them the
+    B200 primitives;
+  * sampled bitstrings are always formatted with ``n_qubits`` characters (the reference inherits upstream
+    ``QuasiDistribution.binary_probabilities()``'s pad-to-longest-observed quirk, which can make
+    ``BitstringEvaluator`` raise on short strings: expectation_calculation.py:96, bitstring_evaluation.py:29-32).
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Optional
+
+import numpy as np
+
+from . import expectation as ex
+from .containers import QuasiDistribution
+from .engine import operator_terms
+from .primitives import B200EstimatorV2, B200SamplerV2
+
+
+class CircuitEvaluatorException(Exception):
+    """Raised when a circuit evaluation fails (circuit_evaluation.py:90-91)."""
+
+
+try:  # subclass the reference ABC when it is importable so isinstance() checks in user code keep working
+    from queasars.circuit_evaluation.circuit_evaluation import BaseCircuitEvaluator as _ReferenceBase  # type: ignore
+except Exception:  # pragma: no cover - reference package absent
+    _ReferenceBase = None
+
+
+class BaseCircuitEvaluator(ABC):
+    @abstractmethod
+    def evaluate_circuits(self, circuits: list, parameter_values: list[list[float]]) -> list[float]:
+        ...
+
+    @property
+    @abstractmethod
+    def n_qubits(self) -> int:
+        ...
+
+
+if _ReferenceBase is not None:
+    _ReferenceBase.register(BaseCircuitEvaluator)
+
+
+def measure_quasi_distributions(circuits: list, parameter_values: list[list[float]], sampler, shots: int) -> list[QuasiDistribution]:
+    """Same contract as circuit_evaluation.py:29-59.  With a ``B200SamplerV2`` the ``measure_all`` copy and the
+    per-pub primitive round trip are skipped (sampling the full register *is* measure_all); any other
+    SamplerV2 goes through the generic pub path exactly like the reference."""
+    if isinstance(sampler, B200SamplerV2):
+        pairs = [(c, p) for c, p in zip(circuits, parameter_values) if c is not None and p is not None]
+        idx = sampler.sample_indices([c for c, _ in pairs], [p for _, p in pairs], shots)
+        out = []
+        for row in idx:
+            vals, cnts = np.unique(row, return_counts=True)
+            out.append(QuasiDistribution({int(v): int(c) / shots for v, c in zip(vals, cnts)}, shots=shots))
+        return out
+    measured = [circuit.measure_all(inplace=False) for circuit in circuits]
+    pubs = tuple((c, p) for c, p in zip(measured, parameter_values) if c is not None and p is not None)
+    result = sampler.run(pubs=pubs, shots=shots).result()
+    return [
+        QuasiDistribution({state: count / shots for state, count in res.data["meas"].get_counts().items()}, shots=shots)
+        for res in result
+    ]
+
+
+def _check_initial_state(initial_state_circuit, n_qubits: int, what: str) -> None:
+    if initial_state_circuit is not None and initial_state_circuit.num_qubits != n_qubits:
+        raise ValueError(
+            f"The amount of qubits in the initial state circuit ({initial_state_circuit.num_qubits} "
+            + f"does not match {what} ({n_qubits})"
+        )
+
+
+class _WithInitialState:
+    _initial_state_circuit = None
+
+    def _prepend(self, circuits: list) -> list:
+        """``initial_state_circuit.compose(circuit, inplace=False)`` per circuit (circuit_evaluation.py:148-149),
+        memoised per circuit object so the plan cache (keyed by identity) still hits on repeated calls."""
+        if self._initial_state_circuit is None:
+            return circuits
+        cache = self.__dict__.setdefault("_composed", {})
+        out = []
+        for circ in circuits:
+            hit = cache.get(id(circ))
+            if hit is None or hit[0] is not circ:
+                if len(cache) > 1024:
+                    cache.clear()
+                hit = cache[id(circ)] = (circ, self._initial_state_circuit.compose(circ, inplace=False))
+            out.append(hit[1])
+        return out
+
+
+class B200OperatorCircuitEvaluator(BaseCircuitEvaluator, _WithInitialState):
+    """<psi(theta)|H|psi(theta)> of every circuit, exact up to the estimator's ``precision`` noise
+    (drop-in for ``OperatorCircuitEvaluator``, circuit_evaluation.py:162-219)."""
+
+    def __init__(self, estimator: B200EstimatorV2, estimator_precision: float, operator, initial_state_circuit=None):
+        if not isinstance(estimator, B200EstimatorV2):
+            raise TypeError("B200OperatorCircuitEvaluator needs a B200EstimatorV2 (it carries device / dtype / seed)")
+        self._estimator = estimator
+        self._estimator_precision = float(estimator_precision)
+        self._operator = operator
+        self._n_qubits = int(operator.num_qubits)
+        _check_initial_state(initial_state_circuit, self._n_qubits, "the amount of qubits in the given operator")
+        self._initial_state_circuit = initial_state_circuit
+
+    def evaluate_circuits(self, circuits: list, parameter_values: list[list[float]]) -> list[float]:
+        pairs = [(c, p) for c, p in zip(self._prepend(circuits), parameter_values) if c is not None and p is not None]
+        try:
+            evs = self._estimator.expectation_values([c for c, _ in pairs], [p for _, p in pairs], self._operator)
+        except (ValueError, TypeError):
+            raise
+        except Exception as exc:
+            raise CircuitEvaluatorException(str(exc)) from exc
+        if self._estimator_precision:
+            evs = [float(self._estimator._noisy(np.asarray(e), self._estimator_precision)) for e in evs]
+        return [float(e) for e in evs]
+
+    @property
+    def n_qubits(self) -> int:
+        return self._n_qubits
+
+
+class _SamplerEvaluator(BaseCircuitEvaluator, _WithInitialState):
+    def __init__(self, sampler: B200SamplerV2, sampler_shots: int, alpha: float):
+        if not isinstance(sampler, B200SamplerV2):
+            raise TypeError(f"{type(self).__name__} needs a B200SamplerV2 (it carries device / dtype / seed)")
+        self._sampler = sampler
+        self._sampler_shots = int(sampler_shots)
+        ex.check_alpha(alpha)
+        self._alpha = float(alpha)
+
+    def _distributions(self, circuits, parameter_values):
+        try:
+            return measure_quasi_distributions(self._prepend(circuits), parameter_values, self._sampler, self._sampler_shots)
+        except (ValueError, TypeError):
+            raise
+        except Exception as exc:
+            raise CircuitEvaluatorException(str(exc)) from exc
+
+
+class B200OperatorSamplerCircuitEvaluator(_SamplerEvaluator):
+    """Shots -> distribution -> diagonal-operator expectation / CVaR(alpha)
+    (drop-in for ``OperatorSamplerCircuitEvaluator``, circuit_evaluation.py:94-159)."""
+
+    def __init__(self, sampler: B200SamplerV2, sampler_shots: int, operator, alpha: float = 1.0, initial_state_circuit=None):
+        if not (hasattr(operator, "to_list") or hasattr(operator, "masks")) or not hasattr(operator, "num_qubits"):
+            raise ValueError("If using a sampler to estimate the expectation value, the operator must be a SparsePauliOp!")
+        super().__init__(sampler, sampler_shots, alpha)
+        self._operator = operator
+        n, x, z, c = operator_terms(operator)
+        if np.any(x):
+            raise ValueError("Operator string contains non-diagonal terms")  # [upstream] sampled_expectation_value
+        self._n_qubits, self._z_masks, self._coeffs = n, z, np.real(c).astype(np.float64)
+        _check_initial_state(initial_state_circuit, n, "the amount of qubits in the given operator")
+        self._initial_state_circuit = initial_state_circuit
+
+    def evaluate_circuits(self, circuits: list, parameter_values: list[list[float]]) -> list[float]:
+        dists = self._distributions(circuits, parameter_values)
+        out = []
+        for dist in dists:
+            out.append(float(ex.expectation_with_operator(dist, self._z_masks, self._coeffs, self._alpha)))
+        return out
+
+    @property
+    def n_qubits(self) -> int:
+        return self._n_qubits
+
+
+class B200BitstringCircuitEvaluator(_SamplerEvaluator):
+    """Shots -> distribution -> user function on bitstrings -> expectation / CVaR(alpha)
+    (drop-in for ``BitstringCircuitEvaluator``, circuit_evaluation.py:222-291)."""
+
+    def __init__(self, sampler: B200SamplerV2, sampler_shots: int, bitstring_evaluator, alpha: float = 1.0, initial_state_circuit=None):
+        self._bitstring_evaluator = bitstring_evaluator
+        n = int(bitstring_evaluator.input_length)
+        if initial_state_circuit is not None and initial_state_circuit.num_qubits != n:
+            raise ValueError(
+                f"The amount of qubits in the initial state circuit ({initial_state_circuit.num_qubits} "
+                + f"does not match the input length of the BitstringEvaluator ({n})!"
+            )
+        super().__init__(sampler, sampler_shots, alpha)
+        self._initial_state_circuit = initial_state_circuit
+
+    def evaluate_circuits(self, circuits: list, parameter_values: list[list[float]]) -> list[float]:
+        n = self.n_qubits
+        return [
+            float(ex.expectation_with_bitstring_evaluator(dist, self._bitstring_evaluator, self._alpha, num_bits=n))
+            for dist in self._distributions(circuits, parameter_values)
+        ]
+
+    @property
+    def n_qubits(self) -> int:
+        return int(self._bitstring_evaluator.input_length)

@@ -1,0 +1,273 @@
+"""Sweep planner: gate list -> sequence of *sweeps* over the statevector, each a sequence of register
+*passes* -- the static program the CUDA sweep kernel interprets (csrc/qb_kernels.cuh).
+
+Terminology
+  tile     2^k amplitudes (k = TILE_BITS) that one CTA holds on chip; the tile's bit positions are k
+           qubits ``tile_qubits`` (ascending; always containing the LOW_BITS lowest qubits so that every
+           global access is a run of 2^LOW_BITS contiguous amplitudes = 256 B for complex128).
+  sweep    one read + one write of the whole state (2 * 16 B * 2^n for complex128): the unit of HBM
+           traffic.  All gates of a sweep have their *target* among the tile qubits; a control may be any
+           qubit (a control outside the tile is a per-tile predicate).
+  pass     within a sweep, each thread holds 2^r amplitudes (r = REG_BITS) in registers, spanning r tile
+           bits ``reg_bits``; gates targeting those bits are applied in registers.  Passes exchange data
+           through shared memory; the first pass reads global memory directly and the last pass writes
+           it directly, so both must keep the LOW_BITS lowest tile bits as thread (lane) bits to stay
+           coalesced.
+
+Ordering rule: two gates may be reordered iff on every shared qubit both act diagonally (controls and
+DIAG targets).  The planner is a greedy list scheduler under that rule; it never changes the product of
+the circuit's unitaries; reordering commuting gates changes results only at the level of fp rounding.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Sequence
+
+import numpy as np
+
+from .gate_list import DENSE, DIAG, KernelOp
+
+TILE_BITS = 12
+REG_BITS = 4
+LOW_BITS = 4
+MAX_SWEEP_OPS = 112  # csrc/qb_kernels.cuh kMaxSweepOps
+MAX_SWEEP_PASSES = 16  # kMaxSweepPasses
+
+# position kinds in the encoded program
+K_NONE, K_REG, K_THREAD, K_EXT = 0, 1, 2, 3
+
+
+@dataclass
+class PassOp:
+    op_index: int
+    kind: int
+    tgt_kind: int
+    tgt_pos: int
+    ctrl_kind: int
+    ctrl_pos: int
+
+
+@dataclass
+class PassPlan:
+    reg_bits: list[int] = field(default_factory=list)  # tile-local positions held in registers
+    ops: list[PassOp] = field(default_factory=list)
+    thread_bits: list[int] = field(default_factory=list)  # tile-local position of thread-index bit i
+
+
+@dataclass
+class SweepPlan:
+    tile_qubits: list[int]
+    passes: list[PassPlan]
+
+    @property
+    def n_ops(self) -> int:
+        return sum(len(p.ops) for p in self.passes)
+
+
+@dataclass
+class CircuitPlan:
+    n_qubits: int  # logical
+    n_eff: int  # padded to >= tile_bits
+    tile_bits: int
+    reg_bits: int
+    low_bits: int
+    sweeps: list[SweepPlan]
+    n_ops: int
+
+    @property
+    def n_passes(self) -> int:
+        return sum(len(s.passes) for s in self.sweeps)
+
+
+def _select_sweep(ops: Sequence[KernelOp], remaining: list[int], n_eff: int, k: int, low: int, max_ops: int):
+    tile = set(range(min(low, n_eff)))
+    pend_dense: set[int] = set()
+    pend_any: set[int] = set()
+    chosen: list[int] = []
+    rest: list[int] = []
+    for i in remaining:
+        op = ops[i]
+        t, c = op.target, op.control
+        dense = op.kind == DENSE
+        blocked = (t in pend_any) if dense else (t in pend_dense)
+        if c >= 0 and c in pend_dense:
+            blocked = True
+        ok = not blocked and len(chosen) < max_ops
+        if ok and dense and t not in tile:
+            if len(tile) < k:
+                tile.add(t)
+            else:
+                ok = False
+        if ok:
+            chosen.append(i)
+        else:
+            rest.append(i)
+            if dense:
+                pend_dense.add(t)
+            pend_any.add(t)
+            if c >= 0:
+                pend_any.add(c)
+    q = 0
+    while len(tile) < min(k, n_eff):
+        if q not in tile:
+            tile.add(q)
+        q += 1
+    return sorted(tile), chosen, rest
+
+
+def _thread_bit_order(reg: list[int], k: int, low: int) -> list[int]:
+    """Which tile-local bit each thread-index bit carries.  Passes that touch global memory (no low bit in
+    registers) keep ascending order so lanes 0..2^low-1 walk contiguous amplitudes.  Pure shared-memory
+    passes are free to choose: the shared-memory layout XOR-folds the index in groups of three bits
+    (qb_kernels.cuh: swizzle), so lane bits 0-2 are picked from three different (position mod 3) classes
+    whenever possible, which makes the 128-bit accesses of a quarter warp conflict-free."""
+    free = [b for b in range(k) if b not in reg]
+    if not any(b < low for b in reg):
+        return free
+    picked: list[int] = []
+    for cls in range(3):
+        for b in free:
+            if b % 3 == cls and b not in picked:
+                picked.append(b)
+                break
+    return picked + [b for b in free if b not in picked]
+
+
+def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[int], r: int, low: int) -> list[PassPlan]:
+    k = len(tile_qubits)
+    pos = {q: i for i, q in enumerate(tile_qubits)}
+    regs: list[list[int]] = [[]]
+    allow_low: list[bool] = [False]
+    members: list[list[int]] = [[]]
+    last_dense: dict[int, int] = {}
+    last_any: dict[int, int] = {}
+
+    def new_pass(low_ok: bool):
+        regs.append([])
+        allow_low.append(low_ok)
+        members.append([])
+
+    for i in chosen:
+        op = ops[i]
+        t, c = op.target, op.control
+        dense = op.kind == DENSE
+        lo = last_any.get(t, 0) if dense else last_dense.get(t, 0)
+        if c >= 0:
+            lo = max(lo, last_dense.get(c, 0))
+        p = lo
+        if dense:
+            tp = pos[t]
+            while True:
+                if p == len(regs):
+                    new_pass(True)
+                if tp in regs[p] or (len(regs[p]) < r and (allow_low[p] or tp >= low)):
+                    break
+                p += 1
+            if tp not in regs[p]:
+                regs[p].append(tp)
+            last_dense[t] = p
+            last_any[t] = p
+        else:
+            if p == len(regs):
+                new_pass(True)
+            last_any[t] = max(last_any.get(t, 0), p)
+        if c >= 0:
+            last_any[c] = max(last_any.get(c, 0), p)
+        members[p].append(i)
+
+    # the last pass stores straight to global memory: its register bits must avoid the low (lane) bits
+    if any(b < low for b in regs[-1]):
+        new_pass(False)
+    # an empty leading pass is only needed when the next one holds low bits in registers
+    if len(regs) > 1 and not members[0] and not any(b < low for b in regs[1]):
+        regs.pop(0), allow_low.pop(0), members.pop(0)
+
+    passes: list[PassPlan] = []
+    for reg, mem in zip(regs, members):
+        reg = list(reg)
+        cand = k - 1
+        while len(reg) < min(r, k):
+            if cand not in reg:
+                reg.append(cand)
+            cand -= 1
+        reg.sort()
+        plan = PassPlan(reg_bits=reg, thread_bits=_thread_bit_order(reg, k, low))
+        for i in mem:
+            op = ops[i]
+
+            def locate(qubit: int):
+                if qubit not in pos:
+                    return K_EXT, qubit
+                tp = pos[qubit]
+                return (K_REG, reg.index(tp)) if tp in reg else (K_THREAD, tp)
+
+            tk, tpos = locate(op.target)
+            if op.kind == DENSE:
+                assert tk == K_REG
+            ck, cpos = (K_NONE, 0) if op.control < 0 else locate(op.control)
+            plan.ops.append(PassOp(i, op.kind, tk, tpos, ck, cpos))
+        passes.append(plan)
+    return passes
+
+
+def plan_circuit(ops: Sequence[KernelOp], n_qubits: int, tile_bits: int = TILE_BITS, reg_bits: int = REG_BITS, low_bits: int = LOW_BITS) -> CircuitPlan:
+    n_eff = max(n_qubits, tile_bits)
+    remaining = list(range(len(ops)))
+    sweeps: list[SweepPlan] = []
+    while remaining:
+        max_ops = MAX_SWEEP_OPS
+        while True:  # the kernel stages at most MAX_SWEEP_OPS matrices / MAX_SWEEP_PASSES pass records per sweep
+            tile_qubits, chosen, rest = _select_sweep(ops, remaining, n_eff, tile_bits, low_bits, max_ops)
+            passes = _plan_passes(ops, chosen, tile_qubits, reg_bits, low_bits)
+            if len(passes) <= MAX_SWEEP_PASSES or max_ops == 1:
+                break
+            max_ops = max(1, max_ops // 2)
+        remaining = rest
+        sweeps.append(SweepPlan(tile_qubits, passes))
+    if not sweeps:  # empty circuit: one identity sweep so that |0...0> gets materialised
+        tile_qubits = list(range(tile_bits))
+        sweeps.append(SweepPlan(tile_qubits, [PassPlan(reg_bits=list(range(tile_bits - reg_bits, tile_bits)))]))
+    return CircuitPlan(n_qubits, n_eff, tile_bits, reg_bits, low_bits, sweeps, len(ops))
+
+
+# -------------------------------------------------------------------------------------------------
+# flat encoding handed to the C-ABI (layout documented in include/queasars_b200.h)
+# -------------------------------------------------------------------------------------------------
+SWEEP_DTYPE = np.dtype([("tile_qubits", np.int32, (16,)), ("pass_begin", np.int32), ("pass_end", np.int32), ("reserved", np.int32, (2,))], align=True)
+PASS_DTYPE = np.dtype([("reg_bits", np.int32, (4,)), ("op_begin", np.int32), ("op_end", np.int32), ("thread_bits", np.uint8, (8,))], align=True)
+PASSOP_DTYPE = np.dtype(
+    [("op_index", np.int32), ("kind", np.uint8), ("tgt_kind", np.uint8), ("tgt_pos", np.uint8), ("ctrl_kind", np.uint8), ("ctrl_pos", np.uint8), ("pad", np.uint8, (3,))],
+    align=True,
+)
+ANGLE_DTYPE = np.dtype([("slot", np.int32, (4,)), ("coeff", np.float64, (4,)), ("const", np.float64, (4,)), ("kind", np.int32), ("pad", np.int32)], align=True)
+
+
+def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
+    """-> (sweeps, passes, pass_ops, op_angles) structured arrays."""
+    assert plan.tile_bits <= 16 and plan.reg_bits == 4
+    sweeps = np.zeros(len(plan.sweeps), dtype=SWEEP_DTYPE)
+    passes = np.zeros(plan.n_passes, dtype=PASS_DTYPE)
+    pass_ops = np.zeros(max(1, sum(s.n_ops for s in plan.sweeps)), dtype=PASSOP_DTYPE)
+    pi = oi = 0
+    for si, sw in enumerate(plan.sweeps):
+        sweeps[si]["tile_qubits"][: len(sw.tile_qubits)] = sw.tile_qubits
+        sweeps[si]["pass_begin"] = pi
+        for ps in sw.passes:
+            passes[pi]["reg_bits"][:] = ps.reg_bits
+            passes[pi]["thread_bits"][: len(ps.thread_bits)] = ps.thread_bits
+            passes[pi]["op_begin"] = oi
+            for po in ps.ops:
+                rec = pass_ops[oi]
+                rec["op_index"], rec["kind"] = po.op_index, po.kind
+                rec["tgt_kind"], rec["tgt_pos"] = po.tgt_kind, po.tgt_pos
+                rec["ctrl_kind"], rec["ctrl_pos"] = po.ctrl_kind, po.ctrl_pos
+                oi += 1
+            passes[pi]["op_end"] = oi
+            pi += 1
+        sweeps[si]["pass_end"] = pi
+    angles = np.zeros(max(1, len(ops)), dtype=ANGLE_DTYPE)
+    for i, op in enumerate(ops):
+        for j, a in enumerate(op.angles):
+            angles[i]["slot"][j], angles[i]["coeff"][j], angles[i]["const"][j] = a.slot, a.coeff, a.const
+        angles[i]["kind"] = op.kind
+    return sweeps, passes, pass_ops, angles

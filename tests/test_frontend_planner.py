@@ -1,0 +1,202 @@
+"""Host logic: circuit container + gate-list front end + sweep planner, checked against the oracle through
+the NumPy plan interpreter (tests/plan_emulator.py)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import evqe_genome as og
+from oracle import qiskit_semantics as oq
+from queasars_b200 import gate_list as gl
+from queasars_b200 import schedule as sc
+from queasars_b200.circuit import CU3Gate, Parameter, QuantumCircuit, circuit_to_gate
+from tests.plan_emulator import run_program
+
+
+def build_circuit(instructions, n):
+    """oracle-style instruction list -> queasars_b200 QuantumCircuit (named params become Parameters)."""
+    circ = QuantumCircuit(n)
+    cache = {}
+
+    def conv(p):
+        if isinstance(p, str):
+            return cache.setdefault(p, Parameter(p))
+        if isinstance(p, tuple):
+            return cache.setdefault(p[1], Parameter(p[1])) * p[0] + p[2]
+        return p
+
+    for name, qubits, params in instructions:
+        params = [conv(p) for p in params]
+        if name == "cu3":
+            circ.append(CU3Gate(*params), qubits)
+        elif name in ("u", "u3"):
+            circ.u(*params, qubits[0])
+        else:
+            circ._std(name, list(qubits), params)
+    return circ
+
+
+def emulate(gates: gl.GateList, values, k=12, r=4, low=4):
+    plan = sc.plan_circuit(gates.ops, gates.n_qubits, k, r, low)
+    enc = sc.encode_plan(plan, gates.ops)
+    state = run_program(enc, plan.n_eff, k, list(values))
+    assert np.allclose(state[1 << gates.n_qubits :], 0)
+    return state[: 1 << gates.n_qubits], plan
+
+
+@pytest.mark.parametrize("n,layers,seed", [(4, 2, 0), (6, 3, 1), (9, 4, 2), (12, 3, 3), (14, 2, 4)])
+def test_evqe_circuits_through_planner(n, layers, seed):
+    genome, values = og.random_individual(n, layers, True, seed)
+    instr = og.individual_circuit(genome, values)
+    circ = build_circuit(instr, n)
+    assert [p.name for p in circ.parameters] == oq.parameter_names(instr)
+    gates = gl.from_circuit(circ)
+    assert gates.n_params == len(values)
+    want = oq.statevector(instr, n, values)
+    got, plan = emulate(gates, values)
+    np.testing.assert_allclose(got, want, atol=1e-13)
+
+
+@pytest.mark.parametrize("k,r,low", [(6, 4, 2), (7, 4, 3), (8, 4, 4)])
+@pytest.mark.parametrize("n,layers,seed", [(8, 3, 10), (10, 4, 11), (11, 2, 12)])
+def test_small_tiles_exercise_multi_tile_paths(k, r, low, n, layers, seed):
+    genome, values = og.random_individual(n, layers, True, seed)
+    instr = og.individual_circuit(genome, values)
+    gates = gl.from_circuit(build_circuit(instr, n))
+    want = oq.statevector(instr, n, values)
+    got, plan = emulate(gates, values, k, r, low)
+    np.testing.assert_allclose(got, want, atol=1e-13)
+    kinds = {(po.ctrl_kind) for s in plan.sweeps for p in s.passes for po in p.ops}
+    assert len(plan.sweeps) >= 1 and kinds  # program is non-trivial
+
+
+def test_partial_parameterisation_and_direct_genome_path(genome_golden):
+    for entry in genome_golden["population_12q_3l_seed11"]:
+        genome = tuple(tuple(tuple(g) for g in layer) for layer in entry["layers"])
+        values = entry["parameter_values"]
+        lid = entry["partial_layers"][0]
+        instr = og.individual_circuit(genome, values, {lid})
+        layer_values = values[og.layer_value_slice(genome, lid)]
+        assert layer_values == entry["partial_layer_values"]
+        want = oq.statevector(instr, 12, layer_values)
+        gates = gl.from_circuit(build_circuit(instr, 12))
+        got, _ = emulate(gates, layer_values)
+        np.testing.assert_allclose(got, want, atol=1e-13)
+        # fully parameterised circuit with all stored values reproduces the same state (selection path)
+        full = og.individual_circuit(genome, values)
+        got_full, _ = emulate(gl.from_circuit(build_circuit(full, 12)), values)
+        np.testing.assert_allclose(got_full, oq.statevector(full, 12, values), atol=1e-13)
+
+
+class _FakeGate:
+    def __init__(self, qubit_index, n_params, control=None):
+        self.qubit_index = qubit_index
+        self._n = n_params
+        if control is not None:
+            self.control_qubit_index = control
+
+    def n_parameters(self):
+        return self._n
+
+
+def _fake_individual(genome, values):
+    """duck-typed EVQEIndividual (the real class needs /root/reference)."""
+
+    def mk(n_params):
+        return type("G", (_FakeGate,), {"n_parameters": staticmethod(lambda n=n_params: n)})
+
+    layers = []
+    for layer in genome:
+        gates = []
+        for q, gene in enumerate(layer):
+            if gene[0] == "rot":
+                gates.append(mk(3)(q, 3))
+            elif gene[0] == "crot":
+                gates.append(mk(3)(q, 3, gene[1]))
+            else:
+                gates.append(mk(0)(q, 0))
+        layers.append(type("L", (), {"gates": tuple(gates)})())
+    idx, off = {}, 0
+    for i, layer in enumerate(genome):
+        npar = og.layer_n_params(layer)
+        idx[i] = tuple(range(off, off + npar))
+        off += npar
+    return type("I", (), {"layers": tuple(layers), "n_qubits": len(genome[0]), "parameter_values": tuple(values), "layer_parameter_indices": idx})()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_genome_direct_path_equals_circuit_path(seed):
+    n = 11
+    genome, values = og.random_individual(n, 3, True, seed)
+    ind = _fake_individual(genome, values)
+    for layers in (None, {-1}, {0}, {1, 2}):
+        instr = og.individual_circuit(genome, values, layers)
+        via_circuit = gl.from_circuit(build_circuit(instr, n))
+        direct = gl.from_evqe_individual(ind, layers)
+        assert direct.param_names == via_circuit.param_names
+        assert direct.ops == [op for op in via_circuit.ops]
+
+
+def test_transpiled_basis_gates_and_expressions():
+    n = 5
+    a, b = Parameter("a"), Parameter("b")
+    circ = QuantumCircuit(n)
+    circ.h(0), circ.sx(1), circ.rz(a, 1), circ.cx(0, 1), circ.rzz(b * 2 + 0.3, 1, 3), circ.ecr(2, 4)
+    circ.p(-a, 2), circ.cz(2, 3), circ.swap(0, 4), circ.ry(0.4, 3), circ.rx(b, 0), circ.t(1), circ.sdg(2)
+    circ.cp(0.7, 4, 1), circ.crz(a * 0.5, 3, 0), circ.cu(0.1, 0.2, 0.3, 0.4, 1, 2), circ.rzx(0.9, 0, 2), circ.rxx(a, 3, 4)
+    circ.y(0), circ.z(1), circ.x(2), circ.s(3), circ.tdg(4), circ.barrier(), circ.id(0)
+    instr = []
+    for inst in circ.data:
+        ps = []
+        for p in inst.operation.params:
+            if hasattr(p, "parameters") and p.parameters:
+                (prm,) = p.parameters
+                ps.append((p._terms[prm], prm.name, p._const))
+            else:
+                ps.append(float(p))
+        instr.append((inst.operation.name, tuple(q._index for q in inst.qubits), tuple(ps)))
+    values = [0.37, -1.2]
+    want = oq.statevector(instr, n, values)
+    gates = gl.from_circuit(circ)
+    assert gates.param_names == ("a", "b")
+    got, _ = emulate(gates, values)
+    np.testing.assert_allclose(got, want, atol=1e-13)  # exact including global phase
+
+
+def test_composite_gate_decompose_and_compose():
+    layer = QuantumCircuit(3, name="layer_0")
+    t0, t1 = Parameter("layer0_q0_theta"), Parameter("layer0_q2_theta")
+    layer.u(t0, 0.1, 0.2, 0)
+    layer.append(CU3Gate(t1, 0.3, 0.4), (1, 2))
+    outer = QuantumCircuit(3)
+    outer.append(circuit_to_gate(layer), range(3))
+    flat = outer.decompose()
+    assert [i.operation.name for i in flat.data] == ["u", "cu3"]
+    g1 = gl.from_circuit(outer)  # expands through .definition
+    g2 = gl.from_circuit(flat)
+    assert g1.ops == g2.ops and g1.param_names == ("layer0_q0_theta", "layer0_q2_theta")
+    init = QuantumCircuit(3)
+    init.h(0), init.h(1), init.h(2)
+    composed = init.compose(flat, inplace=False)
+    assert len(init.data) == 3 and len(composed.data) == 5
+    measured = composed.measure_all(inplace=False)
+    assert len(gl.from_circuit(measured).ops) == len(gl.from_circuit(composed).ops)
+    bound = flat.assign_parameters([0.5, 0.6])
+    assert not bound.parameters and gl.from_circuit(bound).n_params == 0
+
+
+def test_planner_invariants():
+    genome, values = og.random_individual(20, 6, True, 3)
+    gates = gl.from_circuit(build_circuit(og.individual_circuit(genome, values), 20))
+    plan = sc.plan_circuit(gates.ops, 20)
+    seen = []
+    for sw in plan.sweeps:
+        assert len(sw.tile_qubits) == 12 and sw.tile_qubits[:4] == [0, 1, 2, 3]
+        assert not any(b < 4 for b in sw.passes[0].reg_bits)
+        assert not any(b < 4 for b in sw.passes[-1].reg_bits)
+        for ps in sw.passes:
+            assert len(set(ps.reg_bits)) == 4
+            seen += [po.op_index for po in ps.ops]
+    assert sorted(seen) == list(range(len(gates.ops)))
+    # a 20-qubit layer needs >= 2 sweeps (16 non-low qubits, 8 per tile); stay close to that bound
+    assert len(plan.sweeps) <= 2 * 6 + 2
