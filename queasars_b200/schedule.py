@@ -226,7 +226,8 @@ def plan_circuit(ops: Sequence[KernelOp], n_qubits: int, tile_bits: int = TILE_B
         sweeps.append(SweepPlan(tile_qubits, passes))
     if not sweeps:  # empty circuit: one identity sweep so that |0...0> gets materialised
         tile_qubits = list(range(tile_bits))
-        sweeps.append(SweepPlan(tile_qubits, [PassPlan(reg_bits=list(range(tile_bits - reg_bits, tile_bits)))]))
+        reg = list(range(tile_bits - reg_bits, tile_bits))
+        sweeps.append(SweepPlan(tile_qubits, [PassPlan(reg_bits=reg, thread_bits=_thread_bit_order(reg, tile_bits, low_bits))]))
     return CircuitPlan(n_qubits, n_eff, tile_bits, reg_bits, low_bits, sweeps, len(ops))
 
 
