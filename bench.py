@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the EVQE circuit-evaluation hot path (BASELINE.json: "EVQE circuit evals/sec at 20q; gate-apply
+HBM GB/s vs peak; at 1/2/4/8 GPU").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--layers L]
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): a population of 32 random EVQE individuals
+(reference generation rules, seed 0 + 1000*rank) on 20 qubits with L parameterised layers, evaluated against a
+synthetic random diagonal Ising Hamiltonian (20 Z + 190 ZZ terms, default_rng(1234)) -- one "step" = one batched
+``evaluate_circuits`` submission of the whole population, i.e. one EVQE selection pass.
+  value   circuit evaluations / s with parameters + plans resident on the device (CUDA events, kernels only)
+  e2e     the same through ``B200OperatorCircuitEvaluator.evaluate_circuits`` with host lists in / floats out
+  roofline  algorithmic bytes (2 * 16 B * 2^n per swept statevector) / CUDA-event time of the sweep kernel
+  gate_apply  the same sweep kernel on ONE 26-qubit state (1 GiB, HBM-resident): the 24-30 q gate-apply figure
+Multi-GPU (torchrun): every rank evaluates its own population of 32 (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_QUBITS = 20
+POPULATION = 32
+METRIC = "evqe_circuit_evals_per_sec_20q"
+UNIT = "circuit_evals/s"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    QUERY = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.proc = None
+        self.path = None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device_index)],
+                stdout=open(self.path, "w"),
+                stderr=subprocess.DEVNULL,
+            )
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        if self.proc is None or not self.path:
+            return None
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1])), smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            return None
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(n_qubits: int, layers: int, population: int, seed: int):
+    from queasars_b200 import genome as gn
+
+    individuals = gn.random_population(n_qubits, layers, population, True, seed)
+    circuits = [ind.to_circuit() for ind in individuals]
+    params = [list(ind.parameter_values) for ind in individuals]
+    return individuals, circuits, params
+
+
+# ---------------------------------------------------------------------------------------------- CPU baseline
+def cpu_evaluate(individuals, table, n_qubits, threads):
+    """Oracle port of the reference path (NumPy restatement of the Qiskit statevector estimator): simulate each
+    individual, then <H> from the precomputed diagonal table (conservative: the reference evaluates 210 Pauli
+    terms per call instead)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import qiskit_semantics as oq
+
+    def one(ind):
+        instr = []
+        for inst in ind.to_circuit().data:
+            ps = tuple(p.name if hasattr(p, "name") else float(p) for p in inst.operation.params)
+            instr.append((inst.operation.name, tuple(q._index for q in inst.qubits), ps))
+        state = oq.statevector(instr, n_qubits, list(ind.parameter_values))
+        return float(np.dot(state.real**2 + state.imag**2, table))
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        return list(pool.map(one, individuals))
+
+
+def cpu_table(n_qubits):
+    from oracle import qiskit_semantics as oq
+    from queasars_b200 import genome as gn
+
+    _, z, c = gn.ising_operator(n_qubits).masks()
+    return oq.diagonal_table(n_qubits, [(int(a), float(b.real)) for a, b in zip(z, c)])
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation is Qiskit (not installable offline), so this arm
+    times the oracle port of it on the host cores: each step = a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    sample = max(1, min(POPULATION, threads))
+    individuals, _, _ = build_workload(N_QUBITS, args.layers, POPULATION, 0)
+    individuals = individuals[:sample]
+    table = cpu_table(N_QUBITS)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_evaluate(individuals, table, N_QUBITS, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_evaluate(individuals, table, N_QUBITS, threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = f"{sample} of the {POPULATION} individuals per step, NumPy oracle port, {threads} threads, diagonal table prebuilt"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"C2: EVQE population of {POPULATION} individuals x {args.layers} layers, {N_QUBITS}-qubit random diagonal Ising (210 terms), one selection pass per step",
+        "n_qubits": N_QUBITS,
+        "population_per_gpu": POPULATION,
+        "layers": args.layers,
+        "precision": "complex128",
+        "parallelism": f"population-parallel x{n_gpus} (one population per GPU, no collective)",
+        "l2": "working set 32 x 16 MiB = 512 MiB per step > 126 MB L2; no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    from queasars_b200 import B200EstimatorV2, B200OperatorCircuitEvaluator
+    from queasars_b200 import genome as gn
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    individuals, circuits, params = build_workload(N_QUBITS, args.layers, POPULATION, 1000 * rank)
+    operator = gn.ising_operator(N_QUBITS)
+    estimator = B200EstimatorV2(device=local_rank, dtype="complex128", coalesce=False)
+    evaluator = B200OperatorCircuitEvaluator(estimator, 0.0, operator)
+    engine = estimator.engine
+    values = evaluator.evaluate_circuits(circuits, params)  # compiles plans, builds the table
+    assert len(values) == POPULATION and all(np.isfinite(values))
+
+    plans = [estimator._cache.plan_for(c) for c in circuits]
+    ham = estimator.hamiltonian_for(operator)
+    batch = engine.resident_batch(plans, ham)
+    h2d = batch.set_params(params)
+    stream = torch.cuda.ExternalStream(engine.stream, device=torch.device("cuda", local_rank))
+    for _ in range(max(3, args.warmup)):
+        batch.run()
+    resident = batch.read()
+    assert np.allclose(resident, values, rtol=0, atol=1e-12)
+
+    # ---- value: device-resident throughput, CUDA events on the launching stream ----
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = engine.launch_count
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            batch.run()
+        ev1.record(stream)
+        engine.synchronize()
+        torch.cuda.synchronize()
+    gpu_launches = engine.launch_count - launches0
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = ms_total / args.steps
+    value = world * POPULATION * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: public evaluator API, host lists in, floats out (H2D of parameters + D2H of results inside) ----
+    for _ in range(max(3, args.warmup)):
+        evaluator.evaluate_circuits(circuits, params)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = evaluator.evaluate_circuits(circuits, params)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * POPULATION * args.steps / e2e_s
+    assert np.allclose(out, values, rtol=0, atol=1e-12)
+
+    # ---- roofline of the dominant kernel (sweep_kernel<double>), live CUDA events per launch ----
+    peak, peak_kind = measured_peak_gbs()
+    stats = batch.stats()
+    tot_ms, tot_states = 0.0, 0
+    for _ in range(3):
+        ms, states = batch.run_timed()
+        tot_ms += float(ms.sum())
+        tot_states += int(states.sum())
+    sweep_bytes = stats["sweep_bytes"]
+    achieved = sweep_bytes * tot_states / (tot_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm",
+        "kernel": "qb::sweep_kernel<double>",
+        "achieved": achieved,
+        "peak": peak,
+        "peak_kind": peak_kind,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "bytes_per_statevector_sweep": sweep_bytes,
+        "sweeps_per_evaluation": stats["state_sweeps"] / POPULATION,
+        "gates_per_sweep": float(np.mean([p.n_ops for p in plans])) / (stats["state_sweeps"] / POPULATION),
+        "sweep_share_of_step": (tot_ms / 3) / ms_per_step,
+        "note": "20-qubit sweeps fuse ~20 fp64 gates each and are FP64-issue bound, not HBM bound; see gate_apply for 26 q",
+    }
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 * POPULATION, "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(gpu_launches),
+        "roofline": roofline,
+        "clocks": clocks.summary(),
+    }
+
+    if rank == 0 and world == 1 and not args.skip_extras:
+        line["gate_apply"] = gate_apply_probe(engine, estimator, peak, args)
+        line["cpu_baseline"] = cpu_baseline_leg(individuals, args, values)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def gate_apply_probe(engine, estimator, peak, args):
+    """Sweep kernel on one HBM-resident 26-qubit state (1 GiB): achieved GB/s per sweep launch."""
+    from queasars_b200 import genome as gn
+
+    out = {}
+    for n, layers in ((26, args.layers), (28, 2)):
+        ind = gn.Individual.random(n, layers, True, 7)
+        plan = engine.compile(__import__("queasars_b200.gate_list", fromlist=["x"]).from_evqe_individual(ind))
+        ham = engine.hamiltonian(gn.ising_operator(n), build_table=True) if n <= 26 else None
+        rb = engine.resident_batch([plan], ham)
+        rb.set_params([list(ind.parameter_values)])
+        for _ in range(3):
+            rb.run()
+        tot_ms, launches = 0.0, 0
+        for _ in range(5):
+            ms, states = rb.run_timed()
+            tot_ms += float(ms.sum())
+            launches += len(ms)
+        bytes_per = rb.stats()["sweep_bytes"]
+        gbs = bytes_per * launches / (tot_ms * 1e-3) / 1e9
+        out[f"{n}q"] = {
+            "layers": layers,
+            "gates": plan.n_ops,
+            "sweeps": plan.n_sweeps,
+            "gates_per_sweep": plan.n_ops / plan.n_sweeps,
+            "ms_per_sweep": tot_ms / launches,
+            "GBps": gbs,
+            "frac_of_measured_hbm": gbs / peak,
+            "evals_per_s": 1e3 / (tot_ms / 5),
+        }
+        rb.close()
+    return out
+
+
+def cpu_baseline_leg(individuals, args, gpu_values):
+    threads = host_threads()
+    sample = max(1, min(len(individuals), threads))
+    table = cpu_table(N_QUBITS)
+    t0 = time.perf_counter()
+    vals = cpu_evaluate(individuals[:sample], table, N_QUBITS, threads)
+    reps = 1
+    while time.perf_counter() - t0 < 10.0 and reps < 8:
+        cpu_evaluate(individuals[:sample], table, N_QUBITS, threads)
+        reps += 1
+    dt = time.perf_counter() - t0
+    err = float(np.max(np.abs(np.asarray(vals) - np.asarray(gpu_values[:sample])) / np.maximum(1.0, np.abs(vals))))
+    return {
+        "value": sample * reps / dt,
+        "unit": UNIT,
+        "cores": threads,
+        "kind": "port",
+        "sample": f"{reps} x {sample} of the {POPULATION} individuals, NumPy oracle port of the Qiskit statevector estimator, diagonal table prebuilt",
+        "max_rel_err_gpu_vs_oracle": err,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--layers", type=int, default=6)
+    ap.add_argument("--skip-extras", action="store_true", help="skip the 26/28-qubit gate-apply probe and the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

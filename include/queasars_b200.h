@@ -150,6 +150,12 @@ int qb_batch_destroy(qb_context* ctx, int64_t batch_id);
 int qb_batch_stats(qb_context* ctx, int64_t batch_id, int64_t* n_sweep_launches, int64_t* n_state_sweeps,
                    int64_t* sweep_bytes, int64_t* n_kernel_launches);
 
+/* Like qb_batch_run, with a CUDA event pair around every sweep-kernel launch (same stream): fills the
+ * device time of each sweep launch in milliseconds and the number of statevectors it swept; synchronises.
+ * Used by bench.py to compute the live roofline of the dominant kernel. */
+int qb_batch_run_timed(qb_context* ctx, int64_t batch_id, int max_launches, float* sweep_ms, int32_t* sweep_states,
+                       int* n_launches);
+
 /* --- device-pointer entry points (parity tests, sharded multi-GPU path) -------------------------------
  * Operate on a caller-owned device statevector of 2^n_local amplitudes.  `index_offset` is OR-ed into the
  * amplitude index seen by QB_K_EXT operands and by the diagonal table lookup, so a rank holding the shard

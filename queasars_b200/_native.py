@@ -49,6 +49,7 @@ def _declare(lib):
         "qb_batch_set_params": [c_void_p, c_int64, c_void_p, c_void_p],
         "qb_batch_run": [c_void_p, c_int64],
         "qb_batch_read": [c_void_p, c_int64, c_void_p],
+        "qb_batch_run_timed": [c_void_p, c_int64, c_int, c_void_p, c_void_p, P(c_int)],
         "qb_batch_destroy": [c_void_p, c_int64],
         "qb_batch_stats": [c_void_p, c_int64, P(c_int64), P(c_int64), P(c_int64), P(c_int64)],
         "qb_apply_plan_device": [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_uint64],
@@ -71,7 +72,7 @@ EXPORTED_SYMBOLS = (
     "qb_context_create qb_context_destroy qb_last_error qb_context_stream qb_context_launch_count "
     "qb_context_set_workspace_limit qb_context_synchronize qb_plan_create qb_plan_destroy qb_hamiltonian_create "
     "qb_hamiltonian_destroy qb_hamiltonian_diag_energies qb_evaluate_expectation qb_sample qb_statevector "
-    "qb_batch_create qb_batch_set_params qb_batch_run qb_batch_read qb_batch_destroy qb_batch_stats "
+    "qb_batch_create qb_batch_set_params qb_batch_run qb_batch_run_timed qb_batch_read qb_batch_destroy qb_batch_stats "
     "qb_apply_plan_device qb_expectation_device qb_record_sizes"
 ).split()
 

@@ -282,20 +282,22 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
     return QB_OK;
 }
 
-template <typename T> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b) {
+template <typename T> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     const size_t smem = qb::sweep_smem_bytes<T>();
     for (int s = 0; s < b.max_sweeps; ++s) {
         dim3 grid(unsigned(b.n_tiles), unsigned(b.active[s]));
+        if (events) QB_CUDA(cudaEventRecord(events[2 * s], ctx->stream));
         qb::sweep_kernel<T><<<grid, qb::kThreads, smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
         QB_TRY(check_launch(ctx, "sweep_kernel"));
+        if (events) QB_CUDA(cudaEventRecord(events[2 * s + 1], ctx->stream));
     }
     return QB_OK;
 }
 
-int launch_circuits(qb_context* ctx, DeviceBatch& b) {
+int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events = nullptr) {
     qb::bind_kernel<<<b.batch, 128, 0, ctx->stream>>>(b.entries.as<qb::BatchEntry>());
     QB_TRY(check_launch(ctx, "bind_kernel"));
-    return b.dtype == QB_C128 ? launch_sweeps_t<double>(ctx, b) : launch_sweeps_t<float>(ctx, b);
+    return b.dtype == QB_C128 ? launch_sweeps_t<double>(ctx, b, events) : launch_sweeps_t<float>(ctx, b, events);
 }
 
 // expectation of one resident state with the generic (non-fused) kernels; result accumulated into d_out[0]
@@ -664,6 +666,31 @@ int qb_batch_run(qb_context* ctx, int64_t batch_id) {
     QB_TRY(launch_circuits(ctx, *b));
     if (b->ham) QB_TRY(launch_expectation(ctx, *b));
     b->launches_per_run = ctx->launches - before;
+    return QB_OK;
+}
+
+int qb_batch_run_timed(qb_context* ctx, int64_t batch_id, int max_launches, float* sweep_ms, int32_t* sweep_states, int* n_launches) {
+    if (!ctx || !sweep_ms || !sweep_states || !n_launches) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    DeviceBatch* b = find_batch(ctx, batch_id);
+    if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
+    if (max_launches < b->max_sweeps) return fail(QB_ERR_INVALID, "output arrays too small");
+    std::vector<cudaEvent_t> events(2 * size_t(b->max_sweeps));
+    for (auto& e : events) QB_CUDA(cudaEventCreate(&e));
+    int rc = launch_circuits(ctx, *b, events.data());
+    if (rc == QB_OK && b->ham) rc = launch_expectation(ctx, *b);
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    if (rc == QB_OK && se == cudaSuccess) {
+        for (int s = 0; s < b->max_sweeps; ++s) {
+            cudaEventElapsedTime(&sweep_ms[s], events[2 * s], events[2 * s + 1]);
+            sweep_states[s] = b->active[s];
+        }
+        *n_launches = b->max_sweeps;
+    }
+    for (auto& e : events) cudaEventDestroy(e);
+    if (rc != QB_OK) return rc;
+    if (se != cudaSuccess) return fail(QB_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(se));
     return QB_OK;
 }
 

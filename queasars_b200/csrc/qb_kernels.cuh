@@ -108,24 +108,47 @@ __device__ __forceinline__ double ld_table(const double* p) {
     return r;
 }
 
-template <typename T, int B>
-__device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[kNReg], const typename Cx<T>::type* __restrict__ m,
-                                            uint32_t cmask) {
+// 2x2 complex matrix on register bit B of the 16 register-resident amplitudes.  CB >= 0: controlled by register
+// bit CB (only the 4 pairs with that bit set are touched); CB < 0: all 8 pairs.  Everything is resolved at compile
+// time so the 8 (4) pair updates are straight-line code the scheduler can interleave (no per-pair predicates).
+template <typename T, int B, int CB>
+__device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[kNReg], const typename Cx<T>::type* __restrict__ m) {
     using C = typename Cx<T>::type;
     const C m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
 #pragma unroll
     for (int j = 0; j < kNReg; ++j) {
         if (j & (1 << B)) continue;
-        if ((j & cmask) == cmask) {
-            const C x = a[j], y = a[j | (1 << B)];
-            C u, v;
-            u.x = m00.x * x.x - m00.y * x.y + m01.x * y.x - m01.y * y.y;
-            u.y = m00.x * x.y + m00.y * x.x + m01.x * y.y + m01.y * y.x;
-            v.x = m10.x * x.x - m10.y * x.y + m11.x * y.x - m11.y * y.y;
-            v.y = m10.x * x.y + m10.y * x.x + m11.x * y.y + m11.y * y.x;
-            a[j] = u;
-            a[j | (1 << B)] = v;
-        }
+        if (CB >= 0 && !(j & (1 << (CB >= 0 ? CB : 0)))) continue;
+        // Term order chosen so that the last FMA of each output reads exactly the register it overwrites:
+        // the update is in place with four temporaries and no register moves at loop / switch merge points.
+        const C x = a[j], y = a[j | (1 << B)];
+        T t0 = m01.x * y.x;
+        T t1 = m01.x * y.y;
+        T t2 = m10.x * x.x;
+        T t3 = m10.x * x.y;
+        t0 = fma(-m01.y, y.y, t0);
+        t1 = fma(m01.y, y.x, t1);
+        t2 = fma(-m10.y, x.y, t2);
+        t3 = fma(m10.y, x.x, t3);
+        t0 = fma(-m00.y, x.y, t0);
+        t1 = fma(m00.y, x.x, t1);
+        t2 = fma(-m11.y, y.y, t2);
+        t3 = fma(m11.y, y.x, t3);
+        a[j].x = fma(m00.x, x.x, t0);
+        a[j].y = fma(m00.x, x.y, t1);
+        a[j | (1 << B)].x = fma(m11.x, y.x, t2);
+        a[j | (1 << B)].y = fma(m11.x, y.y, t3);
+    }
+}
+
+template <typename T, int B>
+__device__ __forceinline__ void apply_dense_ctrl(typename Cx<T>::type (&a)[kNReg], const typename Cx<T>::type* __restrict__ m, int cb) {
+    switch (cb) {
+        case 0: if (B != 0) apply_dense<T, B, (B != 0 ? 0 : 1)>(a, m); break;
+        case 1: if (B != 1) apply_dense<T, B, (B != 1 ? 1 : 0)>(a, m); break;
+        case 2: if (B != 2) apply_dense<T, B, (B != 2 ? 2 : 0)>(a, m); break;
+        case 3: if (B != 3) apply_dense<T, B, (B != 3 ? 3 : 0)>(a, m); break;
+        default: apply_dense<T, B, -1>(a, m); break;
     }
 }
 
@@ -254,11 +277,12 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             else if (po.ctrl_kind == QB_K_EXT) act = (gbase >> po.ctrl_pos) & 1ull;
             if (!act) continue;
             if (po.kind == QB_OP_DENSE) {
+                const int cb = (po.ctrl_kind == QB_K_REG) ? int(po.ctrl_pos) : -1;
                 switch (po.tgt_pos) {
-                    case 0: apply_dense<T, 0>(a, m, cmask); break;
-                    case 1: apply_dense<T, 1>(a, m, cmask); break;
-                    case 2: apply_dense<T, 2>(a, m, cmask); break;
-                    default: apply_dense<T, 3>(a, m, cmask); break;
+                    case 0: apply_dense_ctrl<T, 0>(a, m, cb); break;
+                    case 1: apply_dense_ctrl<T, 1>(a, m, cb); break;
+                    case 2: apply_dense_ctrl<T, 2>(a, m, cb); break;
+                    default: apply_dense_ctrl<T, 3>(a, m, cb); break;
                 }
             } else {
                 const C d0 = m[0], d1 = m[3];

@@ -251,6 +251,15 @@ class ResidentBatch:
     def run(self):
         _native.check(self._engine._lib.qb_batch_run(self._engine._ctx, self.batch_id))
 
+    def run_timed(self):
+        """-> (ms per sweep launch, statevectors swept per launch); CUDA events on the engine's stream."""
+        cap = 4096
+        ms = np.zeros(cap, dtype=np.float32)
+        states = np.zeros(cap, dtype=np.int32)
+        n = ctypes.c_int()
+        _native.check(self._engine._lib.qb_batch_run_timed(self._engine._ctx, self.batch_id, cap, _native.ptr(ms), _native.ptr(states), byref(n)))
+        return ms[: n.value].astype(np.float64), states[: n.value].astype(np.int64)
+
     def read(self) -> np.ndarray:
         out = np.empty(len(self._plans), dtype=np.float64)
         _native.check(self._engine._lib.qb_batch_read(self._engine._ctx, self.batch_id, _native.ptr(out)))
