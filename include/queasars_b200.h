@@ -33,7 +33,7 @@ extern "C" {
 #define QB_C64 1
 
 #define QB_TILE_BITS 12 /* amplitudes per CTA tile = 2^12 */
-#define QB_REG_BITS 4   /* amplitudes per thread   = 2^4  */
+#define QB_REG_BITS 4   /* default amplitudes per thread = 2^4 (a plan may choose 3: 512 threads x 8 amplitudes) */
 #define QB_LOW_BITS 4   /* lowest qubits always inside the tile (256 B contiguous runs for c128) */
 
 /* operand-position kinds inside a pass (see queasars_b200/schedule.py) */
@@ -53,9 +53,9 @@ typedef struct qb_sweep {
 } qb_sweep;
 
 typedef struct qb_pass {
-    int32_t reg_bits[4]; /* tile-local bit positions held in registers */
+    int32_t reg_bits[4]; /* tile-local bit positions held in registers (first reg_bits entries used) */
     int32_t op_begin, op_end;
-    uint8_t thread_bits[8]; /* tile-local bit carried by thread-index bit 0..7 (the 8 non-register bits) */
+    uint8_t thread_bits[12]; /* tile-local bit carried by thread-index bit i (the QB_TILE_BITS - reg_bits others) */
 } qb_pass;
 
 typedef struct qb_pass_op {
@@ -63,7 +63,13 @@ typedef struct qb_pass_op {
     uint8_t kind;     /* QB_OP_*  */
     uint8_t tgt_kind, tgt_pos;
     uint8_t ctrl_kind, ctrl_pos;
-    uint8_t pad[3];
+    /* pre-decoded dispatch (derived from the fields above; checked by qb_plan_create):
+     *   variant     dense: 5 * target_reg_bit + (control_reg_bit + 1)           (0..19)
+     *               diag : 20 = target outside registers, 21 + b = target register bit b, both without a
+     *                      register control; 25 = generic (register-controlled) diagonal
+     *   ctrl_qubit  global qubit index of a QB_K_THREAD / QB_K_EXT control, 0xFF otherwise
+     *   tgt_qubit   global qubit index of a QB_K_THREAD / QB_K_EXT diagonal target, 0xFF otherwise */
+    uint8_t variant, ctrl_qubit, tgt_qubit;
 } qb_pass_op;
 
 /* angle sources of one op: value_j = cnst[j] + coeff[j] * params[slot[j]]  (slot < 0: constant);
@@ -97,7 +103,7 @@ int qb_context_synchronize(qb_context* ctx);
  * Replaces TranspilingEstimatorV2/SamplerV2.run's per-call PassManager.run
  * (circuit_evaluation/transpiling_primitives.py:47, 73-80) and the upstream per-call circuit binding:
  * the circuit is compiled once, parameters are bound on the device at evaluation time. */
-int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int n_params,
+int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n_params,
                    int n_ops, const qb_op_angles* ops,
                    int n_sweeps, const qb_sweep* sweeps,
                    int n_passes, const qb_pass* passes,

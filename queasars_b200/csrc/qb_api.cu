@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point needs a CUDA device and fails with QB_ERR_CUDA otherwise.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -83,7 +84,7 @@ struct HostBuf {  // pinned staging
 };
 
 struct Plan {
-    int n_qubits = 0, n_eff = 0, dtype = 0, n_params = 0, n_ops = 0, n_sweeps = 0;
+    int n_qubits = 0, n_eff = 0, dtype = 0, reg_bits = 4, n_params = 0, n_ops = 0, n_sweeps = 0;
     DevBuf sweeps, passes, pass_ops, angles;
     ~Plan() { sweeps.release(), passes.release(), pass_ops.release(), angles.release(); }
 };
@@ -110,7 +111,7 @@ struct Ham {
 
 // A set of circuit evaluations resident on the device.
 struct DeviceBatch {
-    int batch = 0, n_eff = 0, n_qubits = 0, dtype = 0, max_sweeps = 0;
+    int batch = 0, n_eff = 0, n_qubits = 0, dtype = 0, reg_bits = 4, max_sweeps = 0;
     std::vector<int> order;   // sorted position -> caller index (descending sweep count)
     std::vector<int> active;  // active[s] = number of entries with more than s sweeps
     std::vector<qb::BatchEntry> h_entries;
@@ -193,13 +194,15 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
     for (int i = 0; i < batch; ++i) {
         plans[i] = find_plan(ctx, plan_ids[i]);
         if (!plans[i]) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[i]));
-        if (plans[i]->n_eff != plans[0]->n_eff || plans[i]->dtype != plans[0]->dtype || plans[i]->n_qubits != plans[0]->n_qubits)
-            return fail(QB_ERR_INVALID, "all plans of one batch must share qubit count and dtype");
+        if (plans[i]->n_eff != plans[0]->n_eff || plans[i]->dtype != plans[0]->dtype || plans[i]->n_qubits != plans[0]->n_qubits ||
+            plans[i]->reg_bits != plans[0]->reg_bits)
+            return fail(QB_ERR_INVALID, "all plans of one batch must share qubit count, dtype and register-bit count");
     }
     b.batch = batch;
     b.n_eff = plans[0]->n_eff;
     b.n_qubits = plans[0]->n_qubits;
     b.dtype = plans[0]->dtype;
+    b.reg_bits = plans[0]->reg_bits;
     b.ham = ham;
     if (ham && ham->n_qubits != b.n_qubits)
         return fail(QB_ERR_INVALID, "Hamiltonian acts on " + std::to_string(ham->n_qubits) + " qubits, circuits on " + std::to_string(b.n_qubits));
@@ -282,12 +285,12 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
     return QB_OK;
 }
 
-template <typename T> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
+template <typename T, int R> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     const size_t smem = qb::sweep_smem_bytes<T>();
     for (int s = 0; s < b.max_sweeps; ++s) {
         dim3 grid(unsigned(b.n_tiles), unsigned(b.active[s]));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s], ctx->stream));
-        qb::sweep_kernel<T><<<grid, qb::kThreads, smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
+        qb::sweep_kernel<T, R><<<grid, 1 << (qb::kTileBits - R), smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
         QB_TRY(check_launch(ctx, "sweep_kernel"));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s + 1], ctx->stream));
     }
@@ -297,7 +300,8 @@ template <typename T> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaE
 int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events = nullptr) {
     qb::bind_kernel<<<b.batch, 128, 0, ctx->stream>>>(b.entries.as<qb::BatchEntry>());
     QB_TRY(check_launch(ctx, "bind_kernel"));
-    return b.dtype == QB_C128 ? launch_sweeps_t<double>(ctx, b, events) : launch_sweeps_t<float>(ctx, b, events);
+    if (b.reg_bits == 3) return b.dtype == QB_C128 ? launch_sweeps_t<double, 3>(ctx, b, events) : launch_sweeps_t<float, 3>(ctx, b, events);
+    return b.dtype == QB_C128 ? launch_sweeps_t<double, 4>(ctx, b, events) : launch_sweeps_t<float, 4>(ctx, b, events);
 }
 
 // expectation of one resident state with the generic (non-fused) kernels; result accumulated into d_out[0]
@@ -404,8 +408,10 @@ int qb_context_create(int device, void* stream, qb_context** out) {
         ctx->owns_stream = true;
     }
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_in_done, cudaEventDisableTiming));
-    QB_TRY(configure_kernel(qb::sweep_kernel<double>, qb::sweep_smem_bytes<double>()));
-    QB_TRY(configure_kernel(qb::sweep_kernel<float>, qb::sweep_smem_bytes<float>()));
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, 4>, qb::sweep_smem_bytes<double>()));
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, 4>, qb::sweep_smem_bytes<float>()));
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, 3>, qb::sweep_smem_bytes<double>()));
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, 3>, qb::sweep_smem_bytes<float>()));
     *out = ctx.release();
     return QB_OK;
 }
@@ -442,13 +448,15 @@ int qb_context_synchronize(qb_context* ctx) {
 }
 
 // ---- plans ------------------------------------------------------------------------------------------
-int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int n_params, int n_ops, const qb_op_angles* ops, int n_sweeps,
+int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n_params, int n_ops, const qb_op_angles* ops, int n_sweeps,
                    const qb_sweep* sweeps, int n_passes, const qb_pass* passes, int n_pass_ops, const qb_pass_op* pass_ops,
                    int64_t* plan_id) {
     if (!ctx || !plan_id) return fail(QB_ERR_INVALID, "null argument");
     if (n_qubits < 1 || n_qubits > 40) return fail(QB_ERR_INVALID, "n_qubits out of range");
     if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
     if (n_sweeps < 1 || n_passes < 1) return fail(QB_ERR_INVALID, "a plan needs at least one sweep with one pass");
+    if (reg_bits != 3 && reg_bits != 4) return fail(QB_ERR_INVALID, "reg_bits must be 3 or 4");
+    const int thread_bits = qb::kTileBits - reg_bits;
     const int n_eff = std::max(n_qubits, qb::kTileBits);
     // validate the program: everything the kernel indexes with must be in range
     for (int s = 0; s < n_sweeps; ++s) {
@@ -469,12 +477,12 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int n_params, int n
         for (int p = sw.pass_begin; p < sw.pass_end; ++p) {
             const qb_pass& ps = passes[p];
             uint32_t used = 0;
-            for (int i = 0; i < qb::kRegBits; ++i) {
+            for (int i = 0; i < reg_bits; ++i) {
                 const int b = ps.reg_bits[i];
                 if (b < 0 || b >= qb::kTileBits || ((used >> b) & 1)) return fail(QB_ERR_INVALID, "bad register bit");
                 used |= 1u << b;
             }
-            for (int i = 0; i < qb::kThreadBits; ++i) {
+            for (int i = 0; i < thread_bits; ++i) {
                 const int b = ps.thread_bits[i];
                 if (b >= qb::kTileBits || ((used >> b) & 1)) return fail(QB_ERR_INVALID, "bad thread bit");
                 used |= 1u << b;
@@ -483,16 +491,27 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int n_params, int n
             for (int o = ps.op_begin; o < ps.op_end; ++o) {
                 const qb_pass_op& po = pass_ops[o];
                 if (po.op_index < 0 || po.op_index >= n_ops) return fail(QB_ERR_INVALID, "op index out of range");
-                if (po.kind == QB_OP_DENSE && (po.tgt_kind != QB_K_REG || po.tgt_pos >= qb::kRegBits))
+                if (po.kind == QB_OP_DENSE && (po.tgt_kind != QB_K_REG || po.tgt_pos >= reg_bits))
                     return fail(QB_ERR_INVALID, "dense op target must be a register bit");
                 auto bad = [&](int kind, int pos) {
-                    if (kind == QB_K_REG) return pos >= qb::kRegBits;
+                    if (kind == QB_K_REG) return pos >= reg_bits;
                     if (kind == QB_K_THREAD) return pos >= qb::kTileBits;
                     if (kind == QB_K_EXT) return pos >= 64;
                     return kind != QB_K_NONE;
                 };
                 if (bad(po.tgt_kind, po.tgt_pos) || po.tgt_kind == QB_K_NONE || bad(po.ctrl_kind, po.ctrl_pos))
                     return fail(QB_ERR_INVALID, "bad operand kind/position");
+                // the pre-decoded dispatch fields must agree with the descriptive ones
+                auto gq = [&](int kind, int pos) { return kind == QB_K_THREAD ? sw.tile_qubits[pos] : (kind == QB_K_EXT ? pos : 0xFF); };
+                const int cb = po.ctrl_kind == QB_K_REG ? int(po.ctrl_pos) : -1;
+                int variant, tq = 0xFF;
+                if (po.kind == QB_OP_DENSE) variant = 5 * po.tgt_pos + cb + 1;
+                else if (cb >= 0) variant = 25, tq = gq(po.tgt_kind, po.tgt_pos);
+                else if (po.tgt_kind == QB_K_REG) variant = 21 + po.tgt_pos;
+                else variant = 20, tq = gq(po.tgt_kind, po.tgt_pos);
+                if (po.kind == QB_OP_DENSE && cb == int(po.tgt_pos)) return fail(QB_ERR_INVALID, "control equals target");
+                if (po.variant != variant || po.ctrl_qubit != gq(po.ctrl_kind, po.ctrl_pos) || po.tgt_qubit != tq)
+                    return fail(QB_ERR_INVALID, "pre-decoded dispatch fields are inconsistent");
             }
         }
     }
@@ -503,7 +522,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int n_params, int n
     std::lock_guard<std::mutex> lock(ctx->mu);
     QB_TRY(set_device(ctx));
     auto pl = std::make_unique<Plan>();
-    pl->n_qubits = n_qubits, pl->n_eff = n_eff, pl->dtype = dtype, pl->n_params = n_params, pl->n_ops = n_ops, pl->n_sweeps = n_sweeps;
+    pl->n_qubits = n_qubits, pl->n_eff = n_eff, pl->dtype = dtype, pl->reg_bits = reg_bits, pl->n_params = n_params, pl->n_ops = n_ops, pl->n_sweeps = n_sweeps;
     QB_TRY(upload(ctx, pl->sweeps, sweeps, sizeof(qb_sweep) * size_t(n_sweeps)));
     QB_TRY(upload(ctx, pl->passes, passes, sizeof(qb_pass) * size_t(n_passes)));
     QB_TRY(upload(ctx, pl->pass_ops, pass_ops, sizeof(qb_pass_op) * size_t(n_pass_ops)));

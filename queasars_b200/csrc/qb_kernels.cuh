@@ -23,15 +23,11 @@
 namespace qb {
 
 constexpr int kTileBits = QB_TILE_BITS;
-constexpr int kRegBits = QB_REG_BITS;
-constexpr int kThreadBits = kTileBits - kRegBits;
-constexpr int kThreads = 1 << kThreadBits;  // 256
-constexpr int kNReg = 1 << kRegBits;        // 16 amplitudes per thread
 constexpr int kTileSize = 1 << kTileBits;   // 4096 amplitudes per CTA
+constexpr int kMaxRegBits = 4;
 constexpr int kMaxSweepOps = 112;
 constexpr int kMaxSweepPasses = 16;
 
-static_assert(kRegBits == 4, "register-pass code is written for 4 register bits");
 
 template <typename T> struct Cx;
 template <> struct Cx<double> { using type = double2; };
@@ -55,7 +51,7 @@ struct BatchEntry {
 template <typename T>
 constexpr size_t sweep_smem_bytes() {
     return sizeof(typename Cx<T>::type) * kTileSize + sizeof(T) * 8 * kMaxSweepOps + sizeof(qb_pass_op) * kMaxSweepOps +
-           sizeof(qb_pass) * kMaxSweepPasses;
+           sizeof(qb_pass) * kMaxSweepPasses + sizeof(uint32_t) * (kMaxSweepOps + 1);
 }
 
 // XOR-fold of the tile-local index in groups of three bits: linear over GF(2), so
@@ -111,8 +107,9 @@ __device__ __forceinline__ double ld_table(const double* p) {
 // 2x2 complex matrix on register bit B of the 16 register-resident amplitudes.  CB >= 0: controlled by register
 // bit CB (only the 4 pairs with that bit set are touched); CB < 0: all 8 pairs.  Everything is resolved at compile
 // time so the 8 (4) pair updates are straight-line code the scheduler can interleave (no per-pair predicates).
-template <typename T, int B, int CB>
-__device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[kNReg], const typename Cx<T>::type* __restrict__ m) {
+template <typename T, int R, int B, int CB>
+__device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
+    constexpr int kNReg = 1 << R;
     using C = typename Cx<T>::type;
     const C m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
 #pragma unroll
@@ -141,14 +138,22 @@ __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[kNReg], co
     }
 }
 
-template <typename T, int B>
-__device__ __forceinline__ void apply_dense_ctrl(typename Cx<T>::type (&a)[kNReg], const typename Cx<T>::type* __restrict__ m, int cb) {
-    switch (cb) {
-        case 0: if (B != 0) apply_dense<T, B, (B != 0 ? 0 : 1)>(a, m); break;
-        case 1: if (B != 1) apply_dense<T, B, (B != 1 ? 1 : 0)>(a, m); break;
-        case 2: if (B != 2) apply_dense<T, B, (B != 2 ? 2 : 0)>(a, m); break;
-        case 3: if (B != 3) apply_dense<T, B, (B != 3 ? 3 : 0)>(a, m); break;
-        default: apply_dense<T, B, -1>(a, m); break;
+// dispatch helper: silently ignores (B, CB) combinations that cannot occur for R register bits
+template <typename T, int R, int B, int CB>
+__device__ __forceinline__ void apply_dense_v(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
+    if constexpr (B < R && CB < R && B != CB) apply_dense<T, R, B, CB>(a, m);
+}
+
+template <typename T, int R, int B>
+__device__ __forceinline__ void apply_dense_ctrl(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m, int cb) {
+    if constexpr (B < R) {
+        switch (cb) {
+            case 0: if constexpr (B != 0 && R > 0) apply_dense<T, R, B, 0>(a, m); break;
+            case 1: if constexpr (B != 1 && R > 1) apply_dense<T, R, B, 1>(a, m); break;
+            case 2: if constexpr (B != 2 && R > 2) apply_dense<T, R, B, 2>(a, m); break;
+            case 3: if constexpr (B != 3 && R > 3) apply_dense<T, R, B, 3>(a, m); break;
+            default: apply_dense<T, R, B, -1>(a, m); break;
+        }
     }
 }
 
@@ -160,20 +165,36 @@ __device__ __forceinline__ typename Cx<T>::type cmul(typename Cx<T>::type a, typ
     return r;
 }
 
+// XOR of the per-register-bit offsets selected by the compile-time register index j (global offsets are
+// disjoint bits, swizzled shared-memory offsets are not: XOR is right for both)
+template <int R, typename U>
+__device__ __forceinline__ U reg_offset(int j, const U (&off)[R]) {
+    U r = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+        if (j & (1 << i)) r ^= off[i];
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // sweep kernel: grid = (tiles, active batch entries), block = 256 threads, dynamic smem = sweep_smem_bytes<T>()
 // ---------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 2)
+template <typename T, int R>
+__global__ void __launch_bounds__(1 << (kTileBits - R), (R == 4 ? 2 : 2))
 sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation) {
     using C = typename Cx<T>::type;
+    constexpr int kRegBits = R;
+    constexpr int kThreadBits = kTileBits - R;
+    constexpr int kThreads = 1 << kThreadBits;
+    constexpr int kNReg = 1 << R;
     extern __shared__ __align__(16) unsigned char smem[];
     C* tile = reinterpret_cast<C*>(smem);
     C* s_mat = reinterpret_cast<C*>(smem + sizeof(C) * kTileSize);
     qb_pass_op* s_ops = reinterpret_cast<qb_pass_op*>(smem + sizeof(C) * kTileSize + sizeof(T) * 8 * kMaxSweepOps);
     qb_pass* s_pass = reinterpret_cast<qb_pass*>(reinterpret_cast<unsigned char*>(s_ops) + sizeof(qb_pass_op) * kMaxSweepOps);
+    uint32_t* s_word = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_pass) + sizeof(qb_pass) * kMaxSweepPasses);
     __shared__ qb_sweep s_sweep;
-    __shared__ double s_red[kThreads / 32];
+    __shared__ double s_red[32];
 
     const BatchEntry en = entries[blockIdx.y];  // block-uniform copy into registers
     if (sweep_idx >= en.n_sweeps) return;
@@ -197,6 +218,9 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
         const double* __restrict__ mats = en.matrices;
         for (int i = tid; i < n_sop * 8; i += kThreads)
             s_mat_t[i] = static_cast<T>(mats[size_t(s_ops[i >> 3].op_index) * 8 + (i & 7)]);
+        // pre-decoded dispatch words: variant | ctrl_qubit << 8 | tgt_qubit << 16
+        for (int i = tid; i <= n_sop; i += kThreads)
+            s_word[i] = (i < n_sop) ? (uint32_t(s_ops[i].variant) | (uint32_t(s_ops[i].ctrl_qubit) << 8) | (uint32_t(s_ops[i].tgt_qubit) << 16)) : 0u;
     }
 
     // tile base index: scatter blockIdx.x over the qubits that are not tile bits
@@ -246,14 +270,14 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             if (sweep_idx == 0 && en.init_zero) {
 #pragma unroll
                 for (int j = 0; j < kNReg; ++j) {
-                    const uint64_t idx = g0 | ((j & 1) ? go[0] : 0) | ((j & 2) ? go[1] : 0) | ((j & 4) ? go[2] : 0) | ((j & 8) ? go[3] : 0);
+                    const uint64_t idx = g0 | reg_offset<kRegBits>(j, go);
                     a[j].x = ((idx | en.index_offset) == 0) ? T(1) : T(0);
                     a[j].y = T(0);
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < kNReg; ++j) {
-                    const uint64_t idx = g0 | ((j & 1) ? go[0] : 0) | ((j & 2) ? go[1] : 0) | ((j & 4) ? go[2] : 0) | ((j & 8) ? go[3] : 0);
+                    const uint64_t idx = g0 | reg_offset<kRegBits>(j, go);
                     a[j] = ld_state(st + idx);
                 }
             }
@@ -261,42 +285,65 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
         } else {
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
-                const uint32_t si = s_thr ^ ((j & 1) ? so[0] : 0) ^ ((j & 2) ? so[1] : 0) ^ ((j & 4) ? so[2] : 0) ^ ((j & 8) ? so[3] : 0);
+                const uint32_t si = s_thr ^ reg_offset<kRegBits>(j, so);
                 a[j] = tile[si];
             }
         }
 
         // ---- gates of this pass, applied in registers ----
-        for (int o = ps.op_begin - op_begin; o < ps.op_end - op_begin; ++o) {
-            const qb_pass_op po = s_ops[o];
+        // W = index bits shared by all of this thread's amplitudes: predicates for controls / diagonal targets that
+        // are not register bits are single bit tests on it.
+        const uint64_t W = gbase | g_thr;
+        const int o_end = ps.op_end - op_begin;
+        int o = ps.op_begin - op_begin;
+        uint32_t word_next = s_word[o];
+        for (; o < o_end; ++o) {
+            const uint32_t word = word_next;
+            word_next = s_word[o + 1];  // prefetch the next dispatch word behind this op's arithmetic
+            const uint32_t cq = (word >> 8) & 0xffu;
+            if (cq != 0xffu && !((W >> cq) & 1ull)) continue;
             const C* m = s_mat + o * 4;
-            bool act = true;
-            uint32_t cmask = 0;
-            if (po.ctrl_kind == QB_K_REG) cmask = 1u << po.ctrl_pos;
-            else if (po.ctrl_kind == QB_K_THREAD) act = (e_thr >> po.ctrl_pos) & 1u;
-            else if (po.ctrl_kind == QB_K_EXT) act = (gbase >> po.ctrl_pos) & 1ull;
-            if (!act) continue;
-            if (po.kind == QB_OP_DENSE) {
-                const int cb = (po.ctrl_kind == QB_K_REG) ? int(po.ctrl_pos) : -1;
-                switch (po.tgt_pos) {
-                    case 0: apply_dense_ctrl<T, 0>(a, m, cb); break;
-                    case 1: apply_dense_ctrl<T, 1>(a, m, cb); break;
-                    case 2: apply_dense_ctrl<T, 2>(a, m, cb); break;
-                    default: apply_dense_ctrl<T, 3>(a, m, cb); break;
+            switch (word & 0xffu) {
+#define QB_DENSE_CASES(B)                                                    \
+    case 5 * B + 0: apply_dense_v<T, R, B, -1>(a, m); break;                  \
+    case 5 * B + 1: apply_dense_v<T, R, B, 0>(a, m); break;                   \
+    case 5 * B + 2: apply_dense_v<T, R, B, 1>(a, m); break;                   \
+    case 5 * B + 3: apply_dense_v<T, R, B, 2>(a, m); break;                   \
+    case 5 * B + 4: apply_dense_v<T, R, B, 3>(a, m); break;
+                QB_DENSE_CASES(0)
+                QB_DENSE_CASES(1)
+                QB_DENSE_CASES(2)
+                QB_DENSE_CASES(3)
+#undef QB_DENSE_CASES
+                case 20: {  // diagonal, target bit outside the registers: one factor for all amplitudes
+                    const C d = ((W >> ((word >> 16) & 0xffu)) & 1ull) ? m[3] : m[0];
+#pragma unroll
+                    for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], d);
+                    break;
                 }
-            } else {
-                const C d0 = m[0], d1 = m[3];
-                if (po.tgt_kind == QB_K_REG) {
-                    const uint32_t tb = 1u << po.tgt_pos;
+                case 21: case 22: case 23: case 24: {  // diagonal on a register bit
+                    const uint32_t tb = 1u << ((word & 0xffu) - 21u);
+                    const C d0 = m[0], d1 = m[3];
 #pragma unroll
-                    for (int j = 0; j < kNReg; ++j)
-                        if ((j & cmask) == cmask) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
-                } else {
-                    const bool one = (po.tgt_kind == QB_K_THREAD) ? ((e_thr >> po.tgt_pos) & 1u) : ((gbase >> po.tgt_pos) & 1ull);
-                    const C d = one ? d1 : d0;
+                    for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
+                    break;
+                }
+                default: {  // generic diagonal with a register-bit control (rare: transpiled cz / cp / crz)
+                    const qb_pass_op po = s_ops[o];
+                    const uint32_t cmask = 1u << po.ctrl_pos;
+                    const C d0 = m[0], d1 = m[3];
+                    if (po.tgt_kind == QB_K_REG) {
+                        const uint32_t tb = 1u << po.tgt_pos;
 #pragma unroll
-                    for (int j = 0; j < kNReg; ++j)
-                        if ((j & cmask) == cmask) a[j] = cmul<T>(a[j], d);
+                        for (int j = 0; j < kNReg; ++j)
+                            if (j & cmask) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
+                    } else {
+                        const C d = ((W >> po.tgt_qubit) & 1ull) ? d1 : d0;
+#pragma unroll
+                        for (int j = 0; j < kNReg; ++j)
+                            if (j & cmask) a[j] = cmul<T>(a[j], d);
+                    }
+                    break;
                 }
             }
         }
@@ -306,7 +353,7 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             double acc = 0.0;
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
-                const uint64_t idx = g0 | ((j & 1) ? go[0] : 0) | ((j & 2) ? go[1] : 0) | ((j & 4) ? go[2] : 0) | ((j & 8) ? go[3] : 0);
+                const uint64_t idx = g0 | reg_offset<kRegBits>(j, go);
                 st_state(st + idx, a[j]);
                 if (do_expect) acc += (double(a[j].x) * double(a[j].x) + double(a[j].y) * double(a[j].y)) * ld_table(table + idx);
             }
@@ -318,7 +365,7 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             if (!first) __syncthreads();  // everyone finished reading the previous layout
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
-                const uint32_t si = s_thr ^ ((j & 1) ? so[0] : 0) ^ ((j & 2) ? so[1] : 0) ^ ((j & 4) ? so[2] : 0) ^ ((j & 8) ? so[3] : 0);
+                const uint32_t si = s_thr ^ reg_offset<kRegBits>(j, so);
                 tile[si] = a[j];
             }
             __syncthreads();

@@ -235,17 +235,37 @@ def plan_circuit(ops: Sequence[KernelOp], n_qubits: int, tile_bits: int = TILE_B
 # flat encoding handed to the C-ABI (layout documented in include/queasars_b200.h)
 # -------------------------------------------------------------------------------------------------
 SWEEP_DTYPE = np.dtype([("tile_qubits", np.int32, (16,)), ("pass_begin", np.int32), ("pass_end", np.int32), ("reserved", np.int32, (2,))], align=True)
-PASS_DTYPE = np.dtype([("reg_bits", np.int32, (4,)), ("op_begin", np.int32), ("op_end", np.int32), ("thread_bits", np.uint8, (8,))], align=True)
+PASS_DTYPE = np.dtype([("reg_bits", np.int32, (4,)), ("op_begin", np.int32), ("op_end", np.int32), ("thread_bits", np.uint8, (12,))], align=True)
 PASSOP_DTYPE = np.dtype(
-    [("op_index", np.int32), ("kind", np.uint8), ("tgt_kind", np.uint8), ("tgt_pos", np.uint8), ("ctrl_kind", np.uint8), ("ctrl_pos", np.uint8), ("pad", np.uint8, (3,))],
+    [("op_index", np.int32), ("kind", np.uint8), ("tgt_kind", np.uint8), ("tgt_pos", np.uint8), ("ctrl_kind", np.uint8), ("ctrl_pos", np.uint8), ("variant", np.uint8), ("ctrl_qubit", np.uint8), ("tgt_qubit", np.uint8)],
     align=True,
 )
 ANGLE_DTYPE = np.dtype([("slot", np.int32, (4,)), ("coeff", np.float64, (4,)), ("const", np.float64, (4,)), ("kind", np.int32), ("pad", np.int32)], align=True)
 
 
+def _predecode(po: PassOp, tile_qubits: Sequence[int]) -> tuple[int, int, int]:
+    """(variant, ctrl_qubit, tgt_qubit) of include/queasars_b200.h: the kernel's jump index and the global qubit
+    whose index bit predicates / selects for operands that live outside the registers."""
+
+    def global_qubit(kind: int, pos: int) -> int:
+        if kind == K_THREAD:
+            return tile_qubits[pos]
+        return pos if kind == K_EXT else 0xFF
+
+    cb = po.ctrl_pos if po.ctrl_kind == K_REG else -1
+    cq = global_qubit(po.ctrl_kind, po.ctrl_pos)
+    if po.kind == DENSE:
+        return 5 * po.tgt_pos + (cb + 1), cq, 0xFF
+    if cb >= 0:
+        return 25, cq, global_qubit(po.tgt_kind, po.tgt_pos)
+    if po.tgt_kind == K_REG:
+        return 21 + po.tgt_pos, cq, 0xFF
+    return 20, cq, global_qubit(po.tgt_kind, po.tgt_pos)
+
+
 def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
     """-> (sweeps, passes, pass_ops, op_angles) structured arrays."""
-    assert plan.tile_bits <= 16 and plan.reg_bits == 4
+    assert plan.tile_bits <= 16 and plan.reg_bits in (3, 4)
     sweeps = np.zeros(len(plan.sweeps), dtype=SWEEP_DTYPE)
     passes = np.zeros(plan.n_passes, dtype=PASS_DTYPE)
     pass_ops = np.zeros(max(1, sum(s.n_ops for s in plan.sweeps)), dtype=PASSOP_DTYPE)
@@ -254,7 +274,7 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
         sweeps[si]["tile_qubits"][: len(sw.tile_qubits)] = sw.tile_qubits
         sweeps[si]["pass_begin"] = pi
         for ps in sw.passes:
-            passes[pi]["reg_bits"][:] = ps.reg_bits
+            passes[pi]["reg_bits"][: len(ps.reg_bits)] = ps.reg_bits
             passes[pi]["thread_bits"][: len(ps.thread_bits)] = ps.thread_bits
             passes[pi]["op_begin"] = oi
             for po in ps.ops:
@@ -262,6 +282,7 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
                 rec["op_index"], rec["kind"] = po.op_index, po.kind
                 rec["tgt_kind"], rec["tgt_pos"] = po.tgt_kind, po.tgt_pos
                 rec["ctrl_kind"], rec["ctrl_pos"] = po.ctrl_kind, po.ctrl_pos
+                rec["variant"], rec["ctrl_qubit"], rec["tgt_qubit"] = _predecode(po, sw.tile_qubits)
                 oi += 1
             passes[pi]["op_end"] = oi
             pi += 1

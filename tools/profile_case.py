@@ -16,18 +16,32 @@ ap.add_argument("--layers", type=int, default=6)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--runs", type=int, default=3)
 ap.add_argument("--dtype", default="complex128")
+ap.add_argument("--simple", type=int, default=0, help="instead of an EVQE genome: this many u gates on distinct high qubits, repeated --layers times")
 args = ap.parse_args()
 
 engine = Engine(0, args.dtype)
 inds = gn.random_population(args.n, args.layers, args.batch, True, 7)
-plans = [engine.compile(gl.from_evqe_individual(i)) for i in inds]
+if args.simple:
+    from queasars_b200.circuit import QuantumCircuit
+
+    circ = QuantumCircuit(args.n)
+    for layer in range(args.layers):
+        for g in range(args.simple):
+            circ.u(0.3 + g, 0.2 * layer, 0.1, args.n - 1 - ((g + 8 * layer) % (args.n - 4)))
+    plans = [engine.compile(gl.from_circuit(circ))] * args.batch
+    params = [[] for _ in range(args.batch)]
+else:
+    plans = [engine.compile(gl.from_evqe_individual(i)) for i in inds]
+    params = [list(i.parameter_values) for i in inds]
 ham = engine.hamiltonian(gn.ising_operator(args.n)) if args.n <= 26 else None
 rb = engine.resident_batch(plans, ham)
-rb.set_params([list(i.parameter_values) for i in inds])
+rb.set_params(params)
 for _ in range(args.runs):
     rb.run()
 engine.synchronize()
 ms, states = rb.run_timed()
+gbs = [round(rb.stats()["sweep_bytes"] * int(st) / (float(m) * 1e-3) / 1e9) for m, st in zip(ms, states)]
+print("GB/s per sweep launch", gbs, "passes", [p.n_passes for p in plans][:2])
 print("sweeps", len(ms), "ms", [round(float(m), 4) for m in ms], "states", list(states), "ops", [p.n_ops for p in plans][:4])
 if ham is not None:
     print("values", rb.read()[:4])
