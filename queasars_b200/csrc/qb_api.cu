@@ -64,7 +64,7 @@ struct HostBuf {  // pinned staging
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return QB_OK;
-        if (p) cudaFreeHost(p);
+        if (p) cudaFreeHost(p);  // callers synchronise on the buffer's event before growing it
         p = nullptr;
         cap = 0;
         size_t want = std::max<size_t>(bytes, 1 << 16);
@@ -137,13 +137,15 @@ struct qb_context {
     bool owns_stream = false;
     int sm_count = 148;
     uint64_t workspace_limit = 0;
+    uint64_t default_workspace = uint64_t(8) << 30;  // 80 % of the memory free at creation (cudaMemGetInfo is slow: ask once)
     int64_t launches = 0;
     int64_t next_id = 1;
     std::mutex mu;
     std::map<int64_t, std::unique_ptr<Plan>> plans;
     std::map<int64_t, std::unique_ptr<Ham>> hams;
     std::map<int64_t, std::unique_ptr<DeviceBatch>> batches;
-    HostBuf pin_in, pin_out;
+    HostBuf pin_in, pin_out, pin_entries;
+    cudaEvent_t pin_entries_done = nullptr;
     cudaEvent_t pin_in_done = nullptr;  // last H2D copy out of pin_in
     DevBuf scratch;                     // uniforms / indices / chunk sums / single-state partials
     DeviceBatch oneshot;                // buffers reused by the one-shot entry points (no per-call cudaMalloc)
@@ -264,7 +266,15 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         en.init_zero = init_zero;
         en.index_offset = index_offset;
     }
-    QB_TRY(upload(ctx, b.entries, b.h_entries.data(), sizeof(qb::BatchEntry) * size_t(batch)));
+    {   // entries go through the pinned staging buffer so the copy is truly asynchronous
+        const size_t bytes = sizeof(qb::BatchEntry) * size_t(batch);
+        QB_TRY(b.entries.reserve(bytes));
+        QB_TRY(ctx->pin_entries.reserve(bytes));
+        QB_CUDA(cudaEventSynchronize(ctx->pin_entries_done));
+        std::memcpy(ctx->pin_entries.p, b.h_entries.data(), bytes);
+        QB_CUDA(cudaMemcpyAsync(b.entries.p, ctx->pin_entries.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        QB_CUDA(cudaEventRecord(ctx->pin_entries_done, ctx->stream));
+    }
     return QB_OK;
 }
 
@@ -364,12 +374,7 @@ int batch_read(qb_context* ctx, DeviceBatch& b, double* out_values) {
 
 size_t max_batch_for(qb_context* ctx, const Plan* pl) {
     const size_t state_bytes = (size_t(1) << pl->n_eff) * amp_bytes(pl->dtype);
-    size_t limit = ctx->workspace_limit;
-    if (!limit) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
-        limit = free_b / 10 * 8;
-    }
+    const size_t limit = ctx->workspace_limit ? ctx->workspace_limit : ctx->default_workspace;
     return std::max<size_t>(1, limit / state_bytes);
 }
 
@@ -407,7 +412,12 @@ int qb_context_create(int device, void* stream, qb_context** out) {
         QB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->owns_stream = true;
     }
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->default_workspace = free_b / 10 * 8;
+    }
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_in_done, cudaEventDisableTiming));
+    QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_entries_done, cudaEventDisableTiming));
     QB_TRY(configure_kernel(qb::sweep_kernel<double, 4>, qb::sweep_smem_bytes<double>()));
     QB_TRY(configure_kernel(qb::sweep_kernel<float, 4>, qb::sweep_smem_bytes<float>()));
     QB_TRY(configure_kernel(qb::sweep_kernel<double, 3>, qb::sweep_smem_bytes<double>()));
@@ -425,6 +435,8 @@ int qb_context_destroy(qb_context* ctx) {
     ctx->hams.clear();
     ctx->pin_in.release(), ctx->pin_out.release(), ctx->scratch.release();
     if (ctx->pin_in_done) cudaEventDestroy(ctx->pin_in_done);
+    if (ctx->pin_entries_done) cudaEventDestroy(ctx->pin_entries_done);
+    ctx->pin_entries.release();
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return QB_OK;
