@@ -433,3 +433,24 @@ def test_26q_jssp_sampler_route(engine, jssp_golden):
     assert abs(energies.mean() - exact) < 5 * energies.std() / math.sqrt(shots)
     marg = np.array([np.mean((idx >> q) & 1) for q in range(n)])
     assert np.max(np.abs(marg - np.sin(thetas / 2) ** 2)) < 5 * 0.5 / math.sqrt(shots)
+
+
+# ------------------------------------------------------------------------------------ device-pointer entry points
+def test_sharded_api_single_rank(engine):
+    """ShardedStatevector with one rank drives qb_apply_plan_device / qb_expectation_device on a torch-owned buffer."""
+    import torch
+
+    from queasars_b200.sharded import CudaShardBackend, ShardedStatevector
+
+    n = 14
+    instr, values, circ = evqe_case(n, 3, 8)
+    sv = ShardedStatevector(n, backend=CudaShardBackend(engine), device=torch.device("cuda", 0))
+    sv.run(gl.from_circuit(circ), values)
+    want = oq.statevector(instr, n, values)
+    assert np.max(np.abs(sv.gather_logical() - want)) < 1e-13
+    rng = np.random.default_rng(2)
+    z = [int(v) for v in rng.integers(0, 1 << n, size=7)]
+    c = [float(v) for v in rng.normal(size=7)]
+    e_want = float(np.dot(np.abs(want) ** 2, oq.diagonal_table(n, list(zip(z, c)))))
+    assert rel_err(sv.diagonal_expectation(z, c), e_want) < 1e-10
+    assert abs(sv.norm_squared() - 1.0) < 1e-12

@@ -1,0 +1,83 @@
+"""Sharded-statevector check + timing, one process per GPU:
+   torchrun --nproc-per-node N tools/sharded_check.py --qubits 26 --layers 2
+Rank 0 compares <H> of the sharded run with the single-GPU engine (when the state fits one GPU) and prints
+swap timings (NVLink GB/s per direction per GPU)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+from queasars_b200 import gate_list as gl  # noqa: E402
+from queasars_b200 import genome as gn  # noqa: E402
+from queasars_b200.sharded import ShardedStatevector  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--qubits", dest="n", type=int, default=26)
+ap.add_argument("--layers", type=int, default=2)
+ap.add_argument("--check", type=int, default=1)
+args = ap.parse_args()
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+ind = gn.Individual.random(args.n, args.layers, True, 11)
+gates = gl.from_evqe_individual(ind)
+op = gn.ising_operator(args.n, seed=3)
+_, z, c = op.masks()
+z, c = z[: 2 * args.n], c.real[: 2 * args.n]  # n Z terms + n ZZ terms keep the on-the-fly diagonal kernel cheap
+
+sv = ShardedStatevector(args.n)
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+t0 = time.perf_counter()
+sv.run(gates, ind.parameter_values)
+torch.cuda.synchronize()
+t_run = time.perf_counter() - t0
+t0 = time.perf_counter()
+value = sv.diagonal_expectation(z, c)
+t_exp = time.perf_counter() - t0
+norm = sv.norm_squared()
+
+# swap-only timing
+swap_ms = None
+if world > 1:
+    lp = list(range(sv.n_local - sv.n_global, sv.n_local))
+    for _ in range(2):
+        sv._swap_all_global(lp)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        sv._swap_all_global(lp)
+    e1.record(); torch.cuda.synchronize()
+    swap_ms = e0.elapsed_time(e1) / 4
+
+if rank == 0:
+    out = {"n": args.n, "world": world, "n_local": sv.n_local, "gates": len(gates.ops), "swaps": sv.swaps_done, "value": value,
+           "norm_err": abs(norm - 1.0), "run_s": t_run, "expectation_s": t_exp}
+    if swap_ms is not None:
+        shard_bytes = 16 * (1 << sv.n_local)
+        sent = shard_bytes * (world - 1) / world
+        out.update(swap_ms=swap_ms, swap_sent_GB=sent / 1e9, swap_GBps_per_dir=sent / (swap_ms * 1e-3) / 1e9,
+                   swap_includes="pack + all_to_all_single + unpack")
+    if args.check and args.n <= 30:
+        from queasars_b200.engine import Engine
+        from queasars_b200.operators import SparsePauliOp
+
+        eng = Engine(local)
+        ham = eng.hamiltonian(SparsePauliOp._raw(args.n, [0] * len(z), [int(v) for v in z], [float(v) for v in c]), build_table=False)
+        ref = eng.expectation([eng.compile(gates)], [list(ind.parameter_values)], ham)[0]
+        out["single_gpu_value"] = float(ref)
+        out["rel_err"] = abs(value - ref) / max(1.0, abs(ref))
+    print(json.dumps(out))
+if world > 1:
+    dist.destroy_process_group()
