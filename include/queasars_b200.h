@@ -32,7 +32,8 @@ extern "C" {
 #define QB_C128 0
 #define QB_C64 1
 
-#define QB_TILE_BITS 12 /* amplitudes per CTA tile = 2^12 */
+#define QB_TILE_BITS 11     /* default amplitudes per CTA tile = 2^11 (a plan may choose 12) */
+#define QB_MAX_TILE_BITS 12
 #define QB_REG_BITS 4   /* default amplitudes per thread = 2^4 (a plan may choose 3: 512 threads x 8 amplitudes) */
 #define QB_LOW_BITS 4   /* lowest qubits always inside the tile (256 B contiguous runs for c128) */
 
@@ -47,7 +48,7 @@ extern "C" {
 
 /* --- sweep program records (flat arrays produced by the host-side planner) ------------------------- */
 typedef struct qb_sweep {
-    int32_t tile_qubits[16]; /* QB_TILE_BITS entries used, ascending; tile-local bit i <-> this qubit */
+    int32_t tile_qubits[16]; /* first tile_bits entries used, ascending; tile-local bit i <-> this qubit */
     int32_t pass_begin, pass_end;
     int32_t reserved[2];
 } qb_sweep;
@@ -55,7 +56,7 @@ typedef struct qb_sweep {
 typedef struct qb_pass {
     int32_t reg_bits[4]; /* tile-local bit positions held in registers (first reg_bits entries used) */
     int32_t op_begin, op_end;
-    uint8_t thread_bits[12]; /* tile-local bit carried by thread-index bit i (the QB_TILE_BITS - reg_bits others) */
+    uint8_t thread_bits[12]; /* tile-local bit carried by thread-index bit i (the tile_bits - reg_bits others) */
 } qb_pass;
 
 typedef struct qb_pass_op {
@@ -103,7 +104,7 @@ int qb_context_synchronize(qb_context* ctx);
  * Replaces TranspilingEstimatorV2/SamplerV2.run's per-call PassManager.run
  * (circuit_evaluation/transpiling_primitives.py:47, 73-80) and the upstream per-call circuit binding:
  * the circuit is compiled once, parameters are bound on the device at evaluation time. */
-int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n_params,
+int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int reg_bits, int n_params,
                    int n_ops, const qb_op_angles* ops,
                    int n_sweeps, const qb_sweep* sweeps,
                    int n_passes, const qb_pass* passes,

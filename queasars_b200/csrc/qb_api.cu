@@ -84,7 +84,7 @@ struct HostBuf {  // pinned staging
 };
 
 struct Plan {
-    int n_qubits = 0, n_eff = 0, dtype = 0, reg_bits = 4, n_params = 0, n_ops = 0, n_sweeps = 0;
+    int n_qubits = 0, n_eff = 0, dtype = 0, tile_bits = QB_TILE_BITS, reg_bits = 4, n_params = 0, n_ops = 0, n_sweeps = 0;
     DevBuf sweeps, passes, pass_ops, angles;
     ~Plan() { sweeps.release(), passes.release(), pass_ops.release(), angles.release(); }
 };
@@ -111,7 +111,7 @@ struct Ham {
 
 // A set of circuit evaluations resident on the device.
 struct DeviceBatch {
-    int batch = 0, n_eff = 0, n_qubits = 0, dtype = 0, reg_bits = 4, max_sweeps = 0;
+    int batch = 0, n_eff = 0, n_qubits = 0, dtype = 0, tile_bits = QB_TILE_BITS, reg_bits = 4, max_sweeps = 0;
     std::vector<int> order;   // sorted position -> caller index (descending sweep count)
     std::vector<int> active;  // active[s] = number of entries with more than s sweeps
     std::vector<qb::BatchEntry> h_entries;
@@ -197,19 +197,20 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         plans[i] = find_plan(ctx, plan_ids[i]);
         if (!plans[i]) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[i]));
         if (plans[i]->n_eff != plans[0]->n_eff || plans[i]->dtype != plans[0]->dtype || plans[i]->n_qubits != plans[0]->n_qubits ||
-            plans[i]->reg_bits != plans[0]->reg_bits)
-            return fail(QB_ERR_INVALID, "all plans of one batch must share qubit count, dtype and register-bit count");
+            plans[i]->reg_bits != plans[0]->reg_bits || plans[i]->tile_bits != plans[0]->tile_bits)
+            return fail(QB_ERR_INVALID, "all plans of one batch must share qubit count, dtype and tile / register-bit counts");
     }
     b.batch = batch;
     b.n_eff = plans[0]->n_eff;
     b.n_qubits = plans[0]->n_qubits;
     b.dtype = plans[0]->dtype;
     b.reg_bits = plans[0]->reg_bits;
+    b.tile_bits = plans[0]->tile_bits;
     b.ham = ham;
     if (ham && ham->n_qubits != b.n_qubits)
         return fail(QB_ERR_INVALID, "Hamiltonian acts on " + std::to_string(ham->n_qubits) + " qubits, circuits on " + std::to_string(b.n_qubits));
     b.fuse_expect = ham && ham->diagonal && ham->table.p && ham->table_n_eff == b.n_eff && index_offset == 0;
-    b.n_tiles = size_t(1) << (b.n_eff - qb::kTileBits);
+    b.n_tiles = size_t(1) << (b.n_eff - b.tile_bits);
     b.partial_stride = std::max<size_t>(b.n_tiles, 1024);
 
     b.order.resize(batch);
@@ -295,12 +296,12 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
     return QB_OK;
 }
 
-template <typename T, int R> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
-    const size_t smem = qb::sweep_smem_bytes<T>();
+template <typename T, int R, int K> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
+    const size_t smem = qb::sweep_smem_bytes<T, K>();
     for (int s = 0; s < b.max_sweeps; ++s) {
         dim3 grid(unsigned(b.n_tiles), unsigned(b.active[s]));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s], ctx->stream));
-        qb::sweep_kernel<T, R><<<grid, 1 << (qb::kTileBits - R), smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
+        qb::sweep_kernel<T, R, K><<<grid, 1 << (K - R), smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
         QB_TRY(check_launch(ctx, "sweep_kernel"));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s + 1], ctx->stream));
     }
@@ -310,8 +311,15 @@ template <typename T, int R> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b
 int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events = nullptr) {
     qb::bind_kernel<<<b.batch, 128, 0, ctx->stream>>>(b.entries.as<qb::BatchEntry>());
     QB_TRY(check_launch(ctx, "bind_kernel"));
-    if (b.reg_bits == 3) return b.dtype == QB_C128 ? launch_sweeps_t<double, 3>(ctx, b, events) : launch_sweeps_t<float, 3>(ctx, b, events);
-    return b.dtype == QB_C128 ? launch_sweeps_t<double, 4>(ctx, b, events) : launch_sweeps_t<float, 4>(ctx, b, events);
+#define QB_DISPATCH(R_, K_) \
+    if (b.reg_bits == R_ && b.tile_bits == K_) \
+        return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_>(ctx, b, events) : launch_sweeps_t<float, R_, K_>(ctx, b, events);
+    QB_DISPATCH(4, 11)
+    QB_DISPATCH(4, 12)
+    QB_DISPATCH(3, 11)
+    QB_DISPATCH(3, 12)
+#undef QB_DISPATCH
+    return fail(QB_ERR_INVALID, "unsupported tile / register bit combination");
 }
 
 // expectation of one resident state with the generic (non-fused) kernels; result accumulated into d_out[0]
@@ -418,10 +426,14 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     }
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_in_done, cudaEventDisableTiming));
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_entries_done, cudaEventDisableTiming));
-    QB_TRY(configure_kernel(qb::sweep_kernel<double, 4>, qb::sweep_smem_bytes<double>()));
-    QB_TRY(configure_kernel(qb::sweep_kernel<float, 4>, qb::sweep_smem_bytes<float>()));
-    QB_TRY(configure_kernel(qb::sweep_kernel<double, 3>, qb::sweep_smem_bytes<double>()));
-    QB_TRY(configure_kernel(qb::sweep_kernel<float, 3>, qb::sweep_smem_bytes<float>()));
+#define QB_CONFIGURE(R_, K_)                                                                              \
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, R_, K_>, qb::sweep_smem_bytes<double, K_>())); \
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_>, qb::sweep_smem_bytes<float, K_>()));
+    QB_CONFIGURE(4, 11)
+    QB_CONFIGURE(4, 12)
+    QB_CONFIGURE(3, 11)
+    QB_CONFIGURE(3, 12)
+#undef QB_CONFIGURE
     *out = ctx.release();
     return QB_OK;
 }
@@ -460,7 +472,7 @@ int qb_context_synchronize(qb_context* ctx) {
 }
 
 // ---- plans ------------------------------------------------------------------------------------------
-int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n_params, int n_ops, const qb_op_angles* ops, int n_sweeps,
+int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int reg_bits, int n_params, int n_ops, const qb_op_angles* ops, int n_sweeps,
                    const qb_sweep* sweeps, int n_passes, const qb_pass* passes, int n_pass_ops, const qb_pass_op* pass_ops,
                    int64_t* plan_id) {
     if (!ctx || !plan_id) return fail(QB_ERR_INVALID, "null argument");
@@ -468,8 +480,9 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n
     if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
     if (n_sweeps < 1 || n_passes < 1) return fail(QB_ERR_INVALID, "a plan needs at least one sweep with one pass");
     if (reg_bits != 3 && reg_bits != 4) return fail(QB_ERR_INVALID, "reg_bits must be 3 or 4");
-    const int thread_bits = qb::kTileBits - reg_bits;
-    const int n_eff = std::max(n_qubits, qb::kTileBits);
+    const int thread_bits = tile_bits - reg_bits;
+    if (tile_bits != 11 && tile_bits != 12) return fail(QB_ERR_INVALID, "tile_bits must be 11 or 12");
+    const int n_eff = std::max(n_qubits, tile_bits);
     // validate the program: everything the kernel indexes with must be in range
     for (int s = 0; s < n_sweeps; ++s) {
         const qb_sweep& sw = sweeps[s];
@@ -477,7 +490,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n
             return fail(QB_ERR_INVALID, "sweep " + std::to_string(s) + ": bad pass range");
         if (sw.pass_end - sw.pass_begin > qb::kMaxSweepPasses) return fail(QB_ERR_INVALID, "sweep has too many passes");
         uint64_t mask = 0;
-        for (int i = 0; i < qb::kTileBits; ++i) {
+        for (int i = 0; i < tile_bits; ++i) {
             const int q = sw.tile_qubits[i];
             if (q < 0 || q >= n_eff || ((mask >> q) & 1)) return fail(QB_ERR_INVALID, "sweep " + std::to_string(s) + ": bad tile qubit");
             if (i && q <= sw.tile_qubits[i - 1]) return fail(QB_ERR_INVALID, "tile qubits must ascend");
@@ -491,12 +504,12 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n
             uint32_t used = 0;
             for (int i = 0; i < reg_bits; ++i) {
                 const int b = ps.reg_bits[i];
-                if (b < 0 || b >= qb::kTileBits || ((used >> b) & 1)) return fail(QB_ERR_INVALID, "bad register bit");
+                if (b < 0 || b >= tile_bits || ((used >> b) & 1)) return fail(QB_ERR_INVALID, "bad register bit");
                 used |= 1u << b;
             }
             for (int i = 0; i < thread_bits; ++i) {
                 const int b = ps.thread_bits[i];
-                if (b >= qb::kTileBits || ((used >> b) & 1)) return fail(QB_ERR_INVALID, "bad thread bit");
+                if (b >= tile_bits || ((used >> b) & 1)) return fail(QB_ERR_INVALID, "bad thread bit");
                 used |= 1u << b;
             }
             if (p > sw.pass_begin && ps.op_begin != passes[p - 1].op_end) return fail(QB_ERR_INVALID, "pass op ranges must be contiguous");
@@ -507,7 +520,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n
                     return fail(QB_ERR_INVALID, "dense op target must be a register bit");
                 auto bad = [&](int kind, int pos) {
                     if (kind == QB_K_REG) return pos >= reg_bits;
-                    if (kind == QB_K_THREAD) return pos >= qb::kTileBits;
+                    if (kind == QB_K_THREAD) return pos >= tile_bits;
                     if (kind == QB_K_EXT) return pos >= 64;
                     return kind != QB_K_NONE;
                 };
@@ -534,7 +547,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int reg_bits, int n
     std::lock_guard<std::mutex> lock(ctx->mu);
     QB_TRY(set_device(ctx));
     auto pl = std::make_unique<Plan>();
-    pl->n_qubits = n_qubits, pl->n_eff = n_eff, pl->dtype = dtype, pl->reg_bits = reg_bits, pl->n_params = n_params, pl->n_ops = n_ops, pl->n_sweeps = n_sweeps;
+    pl->n_qubits = n_qubits, pl->n_eff = n_eff, pl->dtype = dtype, pl->tile_bits = tile_bits, pl->reg_bits = reg_bits, pl->n_params = n_params, pl->n_ops = n_ops, pl->n_sweeps = n_sweeps;
     QB_TRY(upload(ctx, pl->sweeps, sweeps, sizeof(qb_sweep) * size_t(n_sweeps)));
     QB_TRY(upload(ctx, pl->passes, passes, sizeof(qb_pass) * size_t(n_passes)));
     QB_TRY(upload(ctx, pl->pass_ops, pass_ops, sizeof(qb_pass_op) * size_t(n_pass_ops)));
@@ -604,7 +617,7 @@ int qb_hamiltonian_create(qb_context* ctx, int n_qubits, int n_terms, const uint
     QB_TRY(upload(ctx, ham->diag_c, dc.data(), sizeof(double) * dc.size()));
     QB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (build_table && ham->n_diag > 0) {
-        const int n_eff = std::max(n_qubits, qb::kTileBits);
+        const int n_eff = std::max(n_qubits, QB_TILE_BITS);
         const uint64_t size = uint64_t(1) << n_eff;
         QB_TRY(ham->table.reserve(sizeof(double) * size));
         ham->table_n_eff = n_eff;

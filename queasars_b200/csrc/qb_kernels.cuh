@@ -22,8 +22,6 @@
 
 namespace qb {
 
-constexpr int kTileBits = QB_TILE_BITS;
-constexpr int kTileSize = 1 << kTileBits;   // 4096 amplitudes per CTA
 constexpr int kMaxRegBits = 4;
 constexpr int kMaxSweepOps = 112;
 constexpr int kMaxSweepPasses = 16;
@@ -48,9 +46,9 @@ struct BatchEntry {
     uint64_t index_offset;
 };
 
-template <typename T>
+template <typename T, int K>
 constexpr size_t sweep_smem_bytes() {
-    return sizeof(typename Cx<T>::type) * kTileSize + sizeof(T) * 8 * kMaxSweepOps + sizeof(qb_pass_op) * kMaxSweepOps +
+    return sizeof(typename Cx<T>::type) * (size_t(1) << K) + sizeof(T) * 8 * kMaxSweepOps + sizeof(qb_pass_op) * kMaxSweepOps +
            sizeof(qb_pass) * kMaxSweepPasses + sizeof(uint32_t) * (kMaxSweepOps + 1);
 }
 
@@ -179,11 +177,13 @@ __device__ __forceinline__ U reg_offset(int j, const U (&off)[R]) {
 // ---------------------------------------------------------------------------------------------------
 // sweep kernel: grid = (tiles, active batch entries), block = 256 threads, dynamic smem = sweep_smem_bytes<T>()
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int R>
-__global__ void __launch_bounds__(1 << (kTileBits - R), (R == 4 ? 2 : 2))
+template <typename T, int R, int K>
+__global__ void __launch_bounds__(1 << (K - R), (K <= 11 ? 4 : 2))
 sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation) {
     using C = typename Cx<T>::type;
     constexpr int kRegBits = R;
+    constexpr int kTileBits = K;
+    constexpr int kTileSize = 1 << K;
     constexpr int kThreadBits = kTileBits - R;
     constexpr int kThreads = 1 << kThreadBits;
     constexpr int kNReg = 1 << R;

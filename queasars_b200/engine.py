@@ -66,12 +66,13 @@ def operator_terms(operator):
 class Engine:
     """One native context (one CUDA device, one stream).  Thread-safe."""
 
-    def __init__(self, device: int = 0, dtype="complex128", stream: Optional[int] = None, workspace_limit: int = 0, reg_bits: Optional[int] = None):
+    def __init__(self, device: int = 0, dtype="complex128", stream: Optional[int] = None, workspace_limit: int = 0, reg_bits: Optional[int] = None, tile_bits: Optional[int] = None):
         self._lib = _native.load()
         self.device = int(device)
         self.dtype = "complex128" if _dtype_code(dtype) == _native.QB_C128 else "complex64"
         self._dtype_code = _dtype_code(dtype)
         self.reg_bits = int(reg_bits if reg_bits is not None else os.environ.get("QB_REG_BITS", schedule.REG_BITS))
+        self.tile_bits = int(tile_bits if tile_bits is not None else os.environ.get("QB_TILE_BITS", schedule.TILE_BITS))
         handle = c_void_p()
         _native.check(self._lib.qb_context_create(self.device, c_void_p(stream) if stream else None, byref(handle)))
         self._ctx = handle
@@ -108,13 +109,13 @@ class Engine:
             hit = self._plan_cache.get(key)
         if hit is not None:
             return hit
-        plan = schedule.plan_circuit(gates.ops, gates.n_qubits, reg_bits=self.reg_bits)
+        plan = schedule.plan_circuit(gates.ops, gates.n_qubits, tile_bits=self.tile_bits, reg_bits=self.reg_bits)
         sweeps, passes, pass_ops, angles = schedule.encode_plan(plan, gates.ops)
         n_pass_ops = sum(s.n_ops for s in plan.sweeps)
         plan_id = c_int64()
         _native.check(
             self._lib.qb_plan_create(
-                self._ctx, gates.n_qubits, code, self.reg_bits, gates.n_params, len(gates.ops), _native.ptr(angles), len(sweeps), _native.ptr(sweeps),
+                self._ctx, gates.n_qubits, code, self.tile_bits, self.reg_bits, gates.n_params, len(gates.ops), _native.ptr(angles), len(sweeps), _native.ptr(sweeps),
                 len(passes), _native.ptr(passes), n_pass_ops, _native.ptr(pass_ops), byref(plan_id),
             )
         )

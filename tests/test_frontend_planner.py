@@ -36,7 +36,7 @@ def build_circuit(instructions, n):
     return circ
 
 
-def emulate(gates: gl.GateList, values, k=12, r=4, low=4):
+def emulate(gates: gl.GateList, values, k=sc.TILE_BITS, r=4, low=4):
     plan = sc.plan_circuit(gates.ops, gates.n_qubits, k, r, low)
     enc = sc.encode_plan(plan, gates.ops)
     state = run_program(enc, plan.n_eff, k, list(values))
@@ -191,7 +191,7 @@ def test_planner_invariants():
     plan = sc.plan_circuit(gates.ops, 20)
     seen = []
     for sw in plan.sweeps:
-        assert len(sw.tile_qubits) == 12 and sw.tile_qubits[:4] == [0, 1, 2, 3]
+        assert len(sw.tile_qubits) == sc.TILE_BITS and sw.tile_qubits[:4] == [0, 1, 2, 3]
         assert not any(b < 4 for b in sw.passes[0].reg_bits)
         assert not any(b < 4 for b in sw.passes[-1].reg_bits)
         for ps in sw.passes:
@@ -200,3 +200,5 @@ def test_planner_invariants():
     assert sorted(seen) == list(range(len(gates.ops)))
     # a 20-qubit layer needs >= 2 sweeps (16 non-low qubits, 8 per tile); stay close to that bound
     assert len(plan.sweeps) <= 2 * 6 + 2
+    plan12 = sc.plan_circuit(gates.ops, 20, tile_bits=12)
+    assert len(plan12.sweeps) <= len(plan.sweeps)
