@@ -109,7 +109,12 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
                    int n_sweeps, const qb_sweep* sweeps,
                    int n_passes, const qb_pass* passes,
                    int n_pass_ops, const qb_pass_op* pass_ops,
+                   const int32_t* init_ops /* max(n_qubits, tile_bits) entries or NULL: product-state start, see below */,
                    int64_t* plan_id);
+/* init_ops[q] >= 0: qubit q starts in the first column of op init_ops[q]'s bound matrix instead of |0> (the planner
+ * peels uncontrolled first gates off the circuit and drops controlled gates whose control is still |0>); the first
+ * sweep then synthesises the product state prod_q v_q[bit_q(k)] instead of |0...0>.  Such ops must not appear in
+ * any pass. */
 int qb_plan_destroy(qb_context* ctx, int64_t plan_id);
 
 /* --- Hamiltonians ---------------------------------------------------------------------------------------

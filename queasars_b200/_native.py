@@ -37,7 +37,7 @@ def _declare(lib):
         "qb_context_launch_count": [c_void_p],
         "qb_context_set_workspace_limit": [c_void_p, c_uint64],
         "qb_context_synchronize": [c_void_p],
-        "qb_plan_create": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, P(c_int64)],
+        "qb_plan_create": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, P(c_int64)],
         "qb_plan_destroy": [c_void_p, c_int64],
         "qb_hamiltonian_create": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, P(c_int64)],
         "qb_hamiltonian_destroy": [c_void_p, c_int64],

@@ -85,8 +85,9 @@ struct HostBuf {  // pinned staging
 
 struct Plan {
     int n_qubits = 0, n_eff = 0, dtype = 0, tile_bits = QB_TILE_BITS, reg_bits = 4, n_params = 0, n_ops = 0, n_sweeps = 0;
-    DevBuf sweeps, passes, pass_ops, angles;
-    ~Plan() { sweeps.release(), passes.release(), pass_ops.release(), angles.release(); }
+    DevBuf sweeps, passes, pass_ops, angles, init_ops;
+    bool has_init = false;
+    ~Plan() { sweeps.release(), passes.release(), pass_ops.release(), angles.release(), init_ops.release(); }
 };
 
 struct Group {
@@ -200,6 +201,9 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
             plans[i]->reg_bits != plans[0]->reg_bits || plans[i]->tile_bits != plans[0]->tile_bits)
             return fail(QB_ERR_INVALID, "all plans of one batch must share qubit count, dtype and tile / register-bit counts");
     }
+    if (!init_zero)
+        for (int i = 0; i < batch; ++i)
+            if (plans[i]->has_init) return fail(QB_ERR_INVALID, "plan was compiled for a |0...0> start (product-state prefix) but is applied to an existing state");
     b.batch = batch;
     b.n_eff = plans[0]->n_eff;
     b.n_qubits = plans[0]->n_qubits;
@@ -256,6 +260,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         en.passes = pl->passes.as<qb_pass>();
         en.pass_ops = pl->pass_ops.as<qb_pass_op>();
         en.angles = pl->angles.as<qb_op_angles>();
+        en.init_ops = pl->has_init ? pl->init_ops.as<int32_t>() : nullptr;
         en.params = b.params.as<double>() + b.param_begin[i];
         en.matrices = b.matrices.as<double>() + 8 * op_begin[i];
         en.state = static_cast<unsigned char*>(b.states.p) + state_bytes * size_t(pos);
@@ -474,7 +479,7 @@ int qb_context_synchronize(qb_context* ctx) {
 // ---- plans ------------------------------------------------------------------------------------------
 int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int reg_bits, int n_params, int n_ops, const qb_op_angles* ops, int n_sweeps,
                    const qb_sweep* sweeps, int n_passes, const qb_pass* passes, int n_pass_ops, const qb_pass_op* pass_ops,
-                   int64_t* plan_id) {
+                   const int32_t* init_ops, int64_t* plan_id) {
     if (!ctx || !plan_id) return fail(QB_ERR_INVALID, "null argument");
     if (n_qubits < 1 || n_qubits > 40) return fail(QB_ERR_INVALID, "n_qubits out of range");
     if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
@@ -543,6 +548,18 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     for (int o = 0; o < n_ops; ++o)
         for (int j = 0; j < 4; ++j)
             if (ops[o].slot[j] >= n_params) return fail(QB_ERR_INVALID, "angle slot out of range");
+    bool has_init = false;
+    if (init_ops) {
+        std::vector<char> used(size_t(std::max(n_ops, 1)), 0);
+        for (int q = 0; q < n_eff; ++q) {
+            if (init_ops[q] < 0) continue;
+            if (init_ops[q] >= n_ops || used[init_ops[q]]) return fail(QB_ERR_INVALID, "bad init op index");
+            used[init_ops[q]] = 1;
+            has_init = true;
+        }
+        for (int o = 0; o < n_pass_ops; ++o)
+            if (used[pass_ops[o].op_index]) return fail(QB_ERR_INVALID, "an init op also appears in a pass");
+    }
 
     std::lock_guard<std::mutex> lock(ctx->mu);
     QB_TRY(set_device(ctx));
@@ -552,6 +569,8 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     QB_TRY(upload(ctx, pl->passes, passes, sizeof(qb_pass) * size_t(n_passes)));
     QB_TRY(upload(ctx, pl->pass_ops, pass_ops, sizeof(qb_pass_op) * size_t(n_pass_ops)));
     QB_TRY(upload(ctx, pl->angles, ops, sizeof(qb_op_angles) * size_t(n_ops)));
+    pl->has_init = has_init;
+    if (has_init) QB_TRY(upload(ctx, pl->init_ops, init_ops, sizeof(int32_t) * size_t(n_eff)));
     QB_CUDA(cudaStreamSynchronize(ctx->stream));
     *plan_id = ctx->next_id++;
     ctx->plans[*plan_id] = std::move(pl);

@@ -102,21 +102,22 @@ class Engine:
         _native.check(self._lib.qb_context_synchronize(self._ctx))
 
     # ------------------------------------------------------------------ compilation
-    def compile(self, gates: GateList, dtype=None) -> PlanHandle:
+    def compile(self, gates: GateList, dtype=None, from_zero_state: bool = True) -> PlanHandle:
+        """``from_zero_state=False``: the plan will be applied to an existing state (no product-state prefix)."""
         code = self._dtype_code if dtype is None else _dtype_code(dtype)
-        key = (code, gates.structure_key())
+        key = (code, bool(from_zero_state), gates.structure_key())
         with self._lock:
             hit = self._plan_cache.get(key)
         if hit is not None:
             return hit
-        plan = schedule.plan_circuit(gates.ops, gates.n_qubits, tile_bits=self.tile_bits, reg_bits=self.reg_bits)
-        sweeps, passes, pass_ops, angles = schedule.encode_plan(plan, gates.ops)
+        plan = schedule.plan_circuit(gates.ops, gates.n_qubits, tile_bits=self.tile_bits, reg_bits=self.reg_bits, product_prefix=from_zero_state)
+        sweeps, passes, pass_ops, angles, init_ops = schedule.encode_plan(plan, gates.ops)
         n_pass_ops = sum(s.n_ops for s in plan.sweeps)
         plan_id = c_int64()
         _native.check(
             self._lib.qb_plan_create(
                 self._ctx, gates.n_qubits, code, self.tile_bits, self.reg_bits, gates.n_params, len(gates.ops), _native.ptr(angles), len(sweeps), _native.ptr(sweeps),
-                len(passes), _native.ptr(passes), n_pass_ops, _native.ptr(pass_ops), byref(plan_id),
+                len(passes), _native.ptr(passes), n_pass_ops, _native.ptr(pass_ops), _native.ptr(init_ops), byref(plan_id),
             )
         )
         handle = PlanHandle(plan_id.value, gates.n_qubits, gates.n_params, len(gates.ops), len(sweeps), len(passes), code)

@@ -73,6 +73,7 @@ class CircuitPlan:
     low_bits: int
     sweeps: list[SweepPlan]
     n_ops: int
+    init_ops: list[int] = field(default_factory=list)  # per (padded) qubit: op giving its initial state, or -1
 
     @property
     def n_passes(self) -> int:
@@ -210,9 +211,48 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
     return passes
 
 
-def plan_circuit(ops: Sequence[KernelOp], n_qubits: int, tile_bits: int = TILE_BITS, reg_bits: int = REG_BITS, low_bits: int = LOW_BITS) -> CircuitPlan:
+def split_product_prefix(ops: Sequence[KernelOp], n_qubits: int) -> tuple[list[int], list[int]]:
+    """Peel the product-state prefix off a circuit that starts in |0...0>.
+
+    Returns ``(init_ops, remaining)``: ``init_ops[q]`` is the index of an uncontrolled op that is the first thing to
+    happen to qubit q (its matrix's first column is qubit q's initial single-qubit state) or -1 (qubit starts in
+    |0>); ``remaining`` are the indices of the ops still to be applied.  Controlled ops whose control qubit has not
+    been touched yet act on control = |0> and are dropped altogether -- in an EVQE circuit that is every ``cu3`` of the
+    first layer (circuit_layer.py:164-189: a control qubit carries no gate of its own in its layer)."""
+    FRESH, PRODUCT, BUSY = 0, 1, 2
+    status = [FRESH] * n_qubits
+    init_ops = [-1] * n_qubits
+    remaining: list[int] = []
+    for i, op in enumerate(ops):
+        t, c = op.target, op.control
+        if c >= 0:
+            if status[c] == FRESH:
+                continue  # control is |0>: identity
+            status[c] = status[t] = BUSY
+            remaining.append(i)
+        elif status[t] == FRESH:
+            status[t] = PRODUCT
+            init_ops[t] = i
+        else:
+            status[t] = BUSY
+            remaining.append(i)
+    return init_ops, remaining
+
+
+def plan_circuit(
+    ops: Sequence[KernelOp],
+    n_qubits: int,
+    tile_bits: int = TILE_BITS,
+    reg_bits: int = REG_BITS,
+    low_bits: int = LOW_BITS,
+    product_prefix: bool = True,
+) -> CircuitPlan:
     n_eff = max(n_qubits, tile_bits)
-    remaining = list(range(len(ops)))
+    if product_prefix:
+        init_ops, remaining = split_product_prefix(ops, n_qubits)
+    else:
+        init_ops, remaining = [-1] * n_qubits, list(range(len(ops)))
+    init_ops = init_ops + [-1] * (n_eff - n_qubits)
     sweeps: list[SweepPlan] = []
     while remaining:
         max_ops = MAX_SWEEP_OPS
@@ -228,7 +268,7 @@ def plan_circuit(ops: Sequence[KernelOp], n_qubits: int, tile_bits: int = TILE_B
         tile_qubits = list(range(tile_bits))
         reg = list(range(tile_bits - reg_bits, tile_bits))
         sweeps.append(SweepPlan(tile_qubits, [PassPlan(reg_bits=reg, thread_bits=_thread_bit_order(reg, tile_bits, low_bits))]))
-    return CircuitPlan(n_qubits, n_eff, tile_bits, reg_bits, low_bits, sweeps, len(ops))
+    return CircuitPlan(n_qubits, n_eff, tile_bits, reg_bits, low_bits, sweeps, len(ops), init_ops)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -264,7 +304,7 @@ def _predecode(po: PassOp, tile_qubits: Sequence[int]) -> tuple[int, int, int]:
 
 
 def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
-    """-> (sweeps, passes, pass_ops, op_angles) structured arrays."""
+    """-> (sweeps, passes, pass_ops, op_angles, init_ops) arrays."""
     assert plan.tile_bits <= 16 and plan.reg_bits in (3, 4)
     sweeps = np.zeros(len(plan.sweeps), dtype=SWEEP_DTYPE)
     passes = np.zeros(plan.n_passes, dtype=PASS_DTYPE)
@@ -292,4 +332,5 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
         for j, a in enumerate(op.angles):
             angles[i]["slot"][j], angles[i]["coeff"][j], angles[i]["const"][j] = a.slot, a.coeff, a.const
         angles[i]["kind"] = op.kind
-    return sweeps, passes, pass_ops, angles
+    init_ops = np.asarray(plan.init_ops if plan.init_ops else [-1] * plan.n_eff, dtype=np.int32)
+    return sweeps, passes, pass_ops, angles, init_ops

@@ -47,7 +47,8 @@ class CudaShardBackend:
         torch.cuda.current_stream(state.device).synchronize()
 
     def apply(self, state, ops: list[KernelOp], params: np.ndarray, n_local: int, n_params: int, index_offset: int, init_zero: bool):
-        plan = self.engine.compile(GateList(n_local, ops, n_params, ()))
+        # controls may sit on rank bits (>= n_local), so the single-register product-state prefix does not apply
+        plan = self.engine.compile(GateList(n_local, ops, n_params, ()), from_zero_state=False)
         self._join_torch_stream(state)
         self.engine.apply_plan_device(plan, params, state.data_ptr(), init_zero, index_offset)
 

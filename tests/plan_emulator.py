@@ -22,11 +22,15 @@ def op_matrix(angle_rec, params):
 
 
 def run_program(encoded, n_eff, tile_bits, params, state=None):
-    sweeps, passes, pass_ops, angles = encoded
+    sweeps, passes, pass_ops, angles, init_ops = encoded
     size = 1 << n_eff
     if state is None:
-        state = np.zeros(size, dtype=np.complex128)
-        state[0] = 1.0
+        state = np.ones(1, dtype=np.complex128)
+        for q in range(n_eff):  # product-state start: qubit q = first column of op init_ops[q] (or |0>)
+            v = np.array([1.0, 0.0], dtype=np.complex128) if init_ops[q] < 0 else op_matrix(angles[init_ops[q]], params)[:, 0]
+            state = np.kron(v, state)
+        used = {int(po["op_index"]) for po in pass_ops[: sum(int(p["op_end"] - p["op_begin"]) for p in passes)]}
+        assert not used & {int(i) for i in init_ops if i >= 0}
     else:
         state = state.copy()
     e = np.arange(1 << tile_bits, dtype=np.int64)

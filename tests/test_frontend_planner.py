@@ -197,7 +197,14 @@ def test_planner_invariants():
         for ps in sw.passes:
             assert len(set(ps.reg_bits)) == 4
             seen += [po.op_index for po in ps.ops]
-    assert sorted(seen) == list(range(len(gates.ops)))
+    absorbed = [i for i in plan.init_ops if i >= 0]
+    init_ops, remaining = sc.split_product_prefix(gates.ops, 20)
+    assert sorted(seen) == remaining and sorted(absorbed) == sorted(i for i in init_ops if i >= 0)
+    dropped = set(range(len(gates.ops))) - set(seen) - set(absorbed)
+    assert all(gates.ops[i].control >= 0 for i in dropped)  # only controlled gates on a |0> control vanish
+    assert len(absorbed) >= 5 and dropped
+    full = sc.plan_circuit(gates.ops, 20, product_prefix=False)
+    assert sorted(po.op_index for sw in full.sweeps for ps in sw.passes for po in ps.ops) == list(range(len(gates.ops)))
     # a 20-qubit layer needs >= 2 sweeps (16 non-low qubits, 8 per tile); stay close to that bound
     assert len(plan.sweeps) <= 2 * 6 + 2
     plan12 = sc.plan_circuit(gates.ops, 20, tile_bits=12)
