@@ -301,12 +301,12 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
     return QB_OK;
 }
 
-template <typename T, int R, int K> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
+template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     const size_t smem = qb::sweep_smem_bytes<T, K>();
     for (int s = 0; s < b.max_sweeps; ++s) {
         dim3 grid(unsigned(b.n_tiles), unsigned(b.active[s]));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s], ctx->stream));
-        qb::sweep_kernel<T, R, K><<<grid, 1 << (K - R), smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
+        qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
         QB_TRY(check_launch(ctx, "sweep_kernel"));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s + 1], ctx->stream));
     }
@@ -316,13 +316,17 @@ template <typename T, int R, int K> int launch_sweeps_t(qb_context* ctx, DeviceB
 int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events = nullptr) {
     qb::bind_kernel<<<b.batch, 128, 0, ctx->stream>>>(b.entries.as<qb::BatchEntry>());
     QB_TRY(check_launch(ctx, "bind_kernel"));
-#define QB_DISPATCH(R_, K_) \
-    if (b.reg_bits == R_ && b.tile_bits == K_) \
-        return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_>(ctx, b, events) : launch_sweeps_t<float, R_, K_>(ctx, b, events);
+    // amplitude indices fit 32 bits up to 31 local qubits: cheaper address arithmetic for the common sizes
+#define QB_DISPATCH(R_, K_)                                                                                           \
+    if (b.reg_bits == R_ && b.tile_bits == K_) {                                                                      \
+        if (b.n_eff <= 31)                                                                                            \
+            return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_, uint32_t>(ctx, b, events)                     \
+                                      : launch_sweeps_t<float, R_, K_, uint32_t>(ctx, b, events);                     \
+        return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_, uint64_t>(ctx, b, events)                         \
+                                  : launch_sweeps_t<float, R_, K_, uint64_t>(ctx, b, events);                         \
+    }
     QB_DISPATCH(4, 11)
     QB_DISPATCH(4, 12)
-    QB_DISPATCH(3, 11)
-    QB_DISPATCH(3, 12)
 #undef QB_DISPATCH
     return fail(QB_ERR_INVALID, "unsupported tile / register bit combination");
 }
@@ -431,13 +435,13 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     }
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_in_done, cudaEventDisableTiming));
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_entries_done, cudaEventDisableTiming));
-#define QB_CONFIGURE(R_, K_)                                                                              \
-    QB_TRY(configure_kernel(qb::sweep_kernel<double, R_, K_>, qb::sweep_smem_bytes<double, K_>())); \
-    QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_>, qb::sweep_smem_bytes<float, K_>()));
+#define QB_CONFIGURE(R_, K_)                                                                                            \
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, R_, K_, uint32_t>, qb::sweep_smem_bytes<double, K_>())); \
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_, uint32_t>, qb::sweep_smem_bytes<float, K_>()));   \
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, R_, K_, uint64_t>, qb::sweep_smem_bytes<double, K_>())); \
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_, uint64_t>, qb::sweep_smem_bytes<float, K_>()));
     QB_CONFIGURE(4, 11)
     QB_CONFIGURE(4, 12)
-    QB_CONFIGURE(3, 11)
-    QB_CONFIGURE(3, 12)
 #undef QB_CONFIGURE
     *out = ctx.release();
     return QB_OK;
@@ -484,7 +488,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     if (n_qubits < 1 || n_qubits > 40) return fail(QB_ERR_INVALID, "n_qubits out of range");
     if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
     if (n_sweeps < 1 || n_passes < 1) return fail(QB_ERR_INVALID, "a plan needs at least one sweep with one pass");
-    if (reg_bits != 3 && reg_bits != 4) return fail(QB_ERR_INVALID, "reg_bits must be 3 or 4");
+    if (reg_bits != 4) return fail(QB_ERR_INVALID, "reg_bits must be 4 (3 is supported by the kernel template but not compiled in)");
     const int thread_bits = tile_bits - reg_bits;
     if (tile_bits != 11 && tile_bits != 12) return fail(QB_ERR_INVALID, "tile_bits must be 11 or 12");
     const int n_eff = std::max(n_qubits, tile_bits);

@@ -23,7 +23,7 @@
 namespace qb {
 
 constexpr int kMaxRegBits = 4;
-constexpr int kMaxSweepOps = 112;
+constexpr int kMaxSweepOps = 96;
 constexpr int kMaxSweepPasses = 16;
 
 
@@ -178,8 +178,9 @@ __device__ __forceinline__ U reg_offset(int j, const U (&off)[R]) {
 // ---------------------------------------------------------------------------------------------------
 // sweep kernel: grid = (tiles, active batch entries), block = 256 threads, dynamic smem = sweep_smem_bytes<T>()
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int R, int K>
+template <typename T, int R, int K, typename Idx>
 __global__ void __launch_bounds__(1 << (K - R), (K <= 11 ? 4 : 2))
+// (K - R <= 8: the scatter tables cover at most 8 thread-index bits)
 sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation) {
     using C = typename Cx<T>::type;
     constexpr int kRegBits = R;
@@ -224,12 +225,14 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             s_word[i] = (i < n_sop) ? (uint32_t(s_ops[i].variant) | (uint32_t(s_ops[i].ctrl_qubit) << 8) | (uint32_t(s_ops[i].tgt_qubit) << 16)) : 0u;
     }
 
-    // tile base index: scatter blockIdx.x over the qubits that are not tile bits
-    uint64_t tile_mask = 0;
-#pragma unroll
-    for (int i = 0; i < kTileBits; ++i) tile_mask |= 1ull << s_sweep.tile_qubits[i];
+    __syncthreads();  // matrices and dispatch words are staged
+    // tile base index = blockIdx.x scattered over the qubits that are not tile bits (every thread, redundantly: cheaper
+    // than serialising it behind a barrier)
     uint64_t base = 0;
     {
+        uint64_t tile_mask = 0;
+#pragma unroll
+        for (int i = 0; i < kTileBits; ++i) tile_mask |= 1ull << s_sweep.tile_qubits[i];
         uint64_t t = blockIdx.x;
         for (int q = 0; q < n_eff; ++q)
             if (!((tile_mask >> q) & 1ull)) {
@@ -259,12 +262,15 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
         const uint32_t s_thr = swz(e_thr);
         uint32_t so[kRegBits];
         uint64_t go[kRegBits];
+        Idx gi[kRegBits];
 #pragma unroll
         for (int i = 0; i < kRegBits; ++i) {
             so[i] = swz(1u << ps.reg_bits[i]);
             go[i] = 1ull << s_sweep.tile_qubits[ps.reg_bits[i]];
+            gi[i] = Idx(go[i]);
         }
         const uint64_t g0 = base | g_thr;
+        const Idx i0 = Idx(g0);
 
         // ---- load ----
         if (first) {
@@ -321,11 +327,10 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             } else {
 #pragma unroll
                 for (int j = 0; j < kNReg; ++j) {
-                    const uint64_t idx = g0 | reg_offset<kRegBits>(j, go);
+                    const Idx idx = i0 | reg_offset<kRegBits>(j, gi);
                     a[j] = ld_state(st + idx);
                 }
             }
-            __syncthreads();  // staged matrices / ops visible before the first compute
         } else {
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
@@ -397,7 +402,7 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             double acc = 0.0;
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
-                const uint64_t idx = g0 | reg_offset<kRegBits>(j, go);
+                const Idx idx = i0 | reg_offset<kRegBits>(j, gi);
                 st_state(st + idx, a[j]);
                 if (do_expect) acc += (double(a[j].x) * double(a[j].x) + double(a[j].y) * double(a[j].y)) * ld_table(table + idx);
             }

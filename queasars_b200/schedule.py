@@ -30,7 +30,7 @@ from .gate_list import DENSE, DIAG, KernelOp
 TILE_BITS = 11  # default; 12 is also compiled (include/queasars_b200.h QB_MAX_TILE_BITS)
 REG_BITS = 4
 LOW_BITS = 4
-MAX_SWEEP_OPS = 112  # csrc/qb_kernels.cuh kMaxSweepOps
+MAX_SWEEP_OPS = 96  # csrc/qb_kernels.cuh kMaxSweepOps
 MAX_SWEEP_PASSES = 16  # kMaxSweepPasses
 
 # position kinds in the encoded program
