@@ -104,7 +104,13 @@ struct Ham {
     std::vector<std::unique_ptr<Group>> groups;  // x == 0 group first (if any), complex weights
     DevBuf table;
     int table_n_eff = 0;
+    // tile-fused evaluation of the non-diagonal groups (expect_tile_kernel); groups that do not fit a tile stay generic
+    std::vector<qb::ExpTileSweep> tile_sweeps;
+    std::vector<int> generic_groups;  // indices into `groups`
+    DevBuf tile_groups, tile_z, tile_wr, tile_wi;
+    int tile_n_eff = 0;
     ~Ham() {
+        tile_groups.release(), tile_z.release(), tile_wr.release(), tile_wi.release();
         diag_z.release(), diag_c.release(), table.release();
         for (auto& g : groups) g->z.release(), g->wr.release(), g->wi.release();
     }
@@ -213,9 +219,9 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
     b.ham = ham;
     if (ham && ham->n_qubits != b.n_qubits)
         return fail(QB_ERR_INVALID, "Hamiltonian acts on " + std::to_string(ham->n_qubits) + " qubits, circuits on " + std::to_string(b.n_qubits));
-    b.fuse_expect = ham && ham->diagonal && ham->table.p && ham->table_n_eff == b.n_eff && index_offset == 0;
+    b.fuse_expect = ham && ham->table.p && ham->table_n_eff == b.n_eff && index_offset == 0;  // diagonal part in the last sweep
     b.n_tiles = size_t(1) << (b.n_eff - b.tile_bits);
-    b.partial_stride = std::max<size_t>(b.n_tiles, 1024);
+    b.partial_stride = std::max<size_t>(size_t(1) << (b.n_eff - std::min(b.n_eff, qb::kExpTileBits)), std::max<size_t>(b.n_tiles, 1024));
 
     b.order.resize(batch);
     std::iota(b.order.begin(), b.order.end(), 0);
@@ -362,22 +368,76 @@ int expectation_state_t(qb_context* ctx, const Ham& ham, const void* d_state, in
     return QB_OK;
 }
 
+// batched <H>: diagonal part from the fused sweep epilogue / table / on-the-fly group, non-diagonal groups tile-fused
+template <typename T> int launch_expectation_t(qb_context* ctx, DeviceBatch& b) {
+    using C = typename qb::Cx<T>::type;
+    const Ham& ham = *b.ham;
+    const uint64_t size = uint64_t(1) << b.n_eff;
+    const C* states = b.states.as<C>();
+    double* partials = b.partials.as<double>();
+    double* out = b.out.as<double>();
+    bool have = false;  // does `out` already hold a value to accumulate onto?
+    auto reduce = [&](int64_t count) -> int {
+        qb::reduce_partials_kernel<<<b.batch, 256, 0, ctx->stream>>>(partials, int64_t(b.partial_stride), count, out, have ? 1 : 0);
+        have = true;
+        return check_launch(ctx, "reduce_partials_kernel");
+    };
+    const int blocks = int(std::min<uint64_t>(1024, std::max<uint64_t>(1, size / 256)));
+    // ---- diagonal part
+    if (b.fuse_expect) {
+        QB_TRY(reduce(int64_t(b.n_tiles)));
+    } else if (ham.n_diag > 0) {
+        const bool table = ham.table.p && ham.table_n_eff == b.n_eff;
+        const Group* dg = ham.groups.front().get();  // the x == 0 group is stored first
+        for (int pos = 0; pos < b.batch; ++pos) {
+            if (table)
+                qb::expect_table_kernel<T><<<blocks, 256, 0, ctx->stream>>>(states + size * pos, ham.table.as<double>(), size,
+                                                                             partials + b.partial_stride * pos);
+            else
+                qb::expect_group_kernel<T><<<blocks, 256, size_t(dg->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double)), ctx->stream>>>(
+                    states + size * pos, size, 0, 0, dg->z.as<uint64_t>(), dg->wr.as<double>(), dg->wi.as<double>(), dg->n_terms,
+                    partials + b.partial_stride * pos);
+            QB_TRY(check_launch(ctx, "diagonal expectation kernel"));
+        }
+        QB_TRY(reduce(blocks));
+    }
+    // ---- non-diagonal groups that fit a tile: one read of every state per tile sweep
+    const bool tiled = !ham.tile_sweeps.empty() && ham.tile_n_eff == b.n_eff;  // (padding differs only below 12 qubits)
+    if (tiled) {
+        const size_t tiles = size_t(1) << (b.n_eff - qb::kExpTileBits);
+        const size_t smem = sizeof(C) << qb::kExpTileBits;
+        for (const auto& sw : ham.tile_sweeps) {
+            dim3 grid(unsigned(tiles), unsigned(b.batch));
+            qb::expect_tile_kernel<T><<<grid, 256, smem, ctx->stream>>>(states, size, b.n_eff, 0, sw, ham.tile_groups.as<qb::ExpTileGroup>(),
+                                                                        ham.tile_z.as<uint64_t>(), ham.tile_wr.as<double>(),
+                                                                        ham.tile_wi.as<double>(), partials, b.partial_stride);
+            QB_TRY(check_launch(ctx, "expect_tile_kernel"));
+            QB_TRY(reduce(int64_t(tiles)));
+        }
+    }
+    // ---- x masks wider than a tile: generic two-read kernel per group
+    std::vector<int> generic = ham.generic_groups;
+    if (!tiled)
+        for (size_t gi = 0; gi < ham.groups.size(); ++gi)
+            if (ham.groups[gi]->xmask != 0 && std::find(generic.begin(), generic.end(), int(gi)) == generic.end()) generic.push_back(int(gi));
+    for (int gi : generic) {
+        const Group* g = ham.groups[gi].get();
+        if (g->xmask >> b.n_eff) return fail(QB_ERR_INVALID, "Pauli term flips a qubit outside the statevector");
+        for (int pos = 0; pos < b.batch; ++pos) {
+            qb::expect_group_kernel<T><<<blocks, 256, size_t(g->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double)), ctx->stream>>>(
+                states + size * pos, size, 0, g->xmask, g->z.as<uint64_t>(), g->wr.as<double>(), g->wi.as<double>(), g->n_terms,
+                partials + b.partial_stride * pos);
+            QB_TRY(check_launch(ctx, "expect_group_kernel"));
+        }
+        QB_TRY(reduce(blocks));
+    }
+    if (!have) QB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * size_t(b.batch), ctx->stream));
+    return QB_OK;
+}
+
 int launch_expectation(qb_context* ctx, DeviceBatch& b) {
     if (!b.ham) return fail(QB_ERR_INVALID, "batch was created without a Hamiltonian");
-    if (b.fuse_expect) {
-        qb::reduce_partials_kernel<<<b.batch, 256, 0, ctx->stream>>>(b.partials.as<double>(), int64_t(b.partial_stride), int64_t(b.n_tiles),
-                                                                      b.out.as<double>(), 0);
-        return check_launch(ctx, "reduce_partials_kernel");
-    }
-    const size_t state_bytes = (size_t(1) << b.n_eff) * amp_bytes(b.dtype);
-    for (int pos = 0; pos < b.batch; ++pos) {
-        const void* st = static_cast<unsigned char*>(b.states.p) + state_bytes * size_t(pos);
-        double* part = b.partials.as<double>() + b.partial_stride * size_t(pos);
-        double* out = b.out.as<double>() + pos;
-        if (b.dtype == QB_C128) QB_TRY(expectation_state_t<double>(ctx, *b.ham, st, b.n_eff, 0, part, out));
-        else QB_TRY(expectation_state_t<float>(ctx, *b.ham, st, b.n_eff, 0, part, out));
-    }
-    return QB_OK;
+    return b.dtype == QB_C128 ? launch_expectation_t<double>(ctx, b) : launch_expectation_t<float>(ctx, b);
 }
 
 int batch_read(qb_context* ctx, DeviceBatch& b, double* out_values) {
@@ -651,6 +711,75 @@ int qb_hamiltonian_create(qb_context* ctx, int n_qubits, int n_terms, const uint
                                                                   ham->diag_c.as<double>(), ham->n_diag);
         QB_TRY(check_launch(ctx, "diag_table_kernel"));
         QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    {   // schedule the non-diagonal x-mask groups into tile sweeps
+        const int K = qb::kExpTileBits, low = QB_LOW_BITS;
+        const int n_eff = std::max(n_qubits, K);
+        ham->tile_n_eff = n_eff;
+        std::vector<int> pending;
+        for (size_t g = 0; g < ham->groups.size(); ++g)
+            if (ham->groups[g]->xmask != 0) pending.push_back(int(g));
+        std::vector<qb::ExpTileGroup> tgroups;
+        std::vector<uint64_t> tz;
+        std::vector<double> twr, twi;
+        std::vector<std::vector<uint64_t>> host_z(ham->groups.size());
+        std::vector<std::vector<double>> host_wr(ham->groups.size()), host_wi(ham->groups.size());
+        for (size_t g = 0; g < xs.size(); ++g) {  // recover host copies of the per-group terms (same order as uploaded)
+            size_t slot = 0;
+            for (; slot < ham->groups.size(); ++slot)
+                if (ham->groups[slot]->xmask == xs[g]) break;
+            for (int t : members[g]) {
+                const int ny = __builtin_popcountll(x_masks[t] & z_masks[t]) & 3;
+                const double re = coeff_re[t], im = coeff_im ? coeff_im[t] : 0.0;
+                double r = re, i = im;
+                if (ny == 1) r = -im, i = re;
+                else if (ny == 2) r = -re, i = -im;
+                else if (ny == 3) r = im, i = -re;
+                host_z[slot].push_back(z_masks[t]), host_wr[slot].push_back(r), host_wi[slot].push_back(i);
+            }
+        }
+        while (!pending.empty()) {
+            uint64_t tile = (uint64_t(1) << low) - 1;
+            std::vector<int> chosen, rest;
+            for (int g : pending) {
+                const uint64_t want = tile | ham->groups[g]->xmask;
+                if (__builtin_popcountll(want) <= K) tile = want, chosen.push_back(g);
+                else rest.push_back(g);
+            }
+            if (chosen.empty()) {  // the first pending group alone does not fit a tile: generic kernel
+                ham->generic_groups.push_back(pending.front());
+                pending.erase(pending.begin());
+                continue;
+            }
+            for (int q = 0; __builtin_popcountll(tile) < K; ++q) tile |= uint64_t(1) << q;
+            qb::ExpTileSweep sw{};
+            int pos_of[64];
+            for (int q = 0, i = 0; q < n_eff; ++q)
+                if ((tile >> q) & 1) pos_of[q] = i, sw.tile_qubits[i++] = q;
+            sw.group_begin = int(tgroups.size());
+            for (int g : chosen) {
+                qb::ExpTileGroup tg{};
+                for (int q = 0; q < n_eff; ++q)
+                    if ((ham->groups[g]->xmask >> q) & 1) tg.xloc |= 1u << pos_of[q];
+                tg.term_begin = int(tz.size());
+                tz.insert(tz.end(), host_z[g].begin(), host_z[g].end());
+                twr.insert(twr.end(), host_wr[g].begin(), host_wr[g].end());
+                twi.insert(twi.end(), host_wi[g].begin(), host_wi[g].end());
+                tg.term_end = int(tz.size());
+                tg.trivial = (host_z[g].size() == 1 && host_z[g][0] == 0) ? 1 : 0;
+                tgroups.push_back(tg);
+            }
+            sw.group_end = int(tgroups.size());
+            ham->tile_sweeps.push_back(sw);
+            pending = rest;
+        }
+        if (!tgroups.empty()) {
+            QB_TRY(upload(ctx, ham->tile_groups, tgroups.data(), sizeof(qb::ExpTileGroup) * tgroups.size()));
+            QB_TRY(upload(ctx, ham->tile_z, tz.data(), sizeof(uint64_t) * tz.size()));
+            QB_TRY(upload(ctx, ham->tile_wr, twr.data(), sizeof(double) * twr.size()));
+            QB_TRY(upload(ctx, ham->tile_wi, twi.data(), sizeof(double) * twi.size()));
+            QB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
     }
     *ham_id = ctx->next_id++;
     ctx->hams[*ham_id] = std::move(ham);

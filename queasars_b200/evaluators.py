@@ -166,15 +166,21 @@ class B200OperatorSamplerCircuitEvaluator(_SamplerEvaluator):
         n, x, z, c = operator_terms(operator)
         if np.any(x):
             raise ValueError("Operator string contains non-diagonal terms")  # [upstream] sampled_expectation_value
-        self._n_qubits, self._z_masks, self._coeffs = n, z, np.real(c).astype(np.float64)
+        self._n_qubits = n
+        self._z_masks, self._coeffs = ex.merge_diagonal_terms(z, np.real(c))
         _check_initial_state(initial_state_circuit, n, "the amount of qubits in the given operator")
         self._initial_state_circuit = initial_state_circuit
 
     def evaluate_circuits(self, circuits: list, parameter_values: list[list[float]]) -> list[float]:
         dists = self._distributions(circuits, parameter_values)
-        out = []
-        for dist in dists:
-            out.append(float(ex.expectation_with_operator(dist, self._z_masks, self._coeffs, self._alpha)))
+        # energies of all distinct sampled states in one device call (E(k) = sum_t c_t (-1)^{popcount(k & z_t)})
+        keys = [np.fromiter(d.keys(), dtype=np.uint64, count=len(d)) for d in dists]
+        ham = self._sampler.hamiltonian_for(self._operator, build_table=False)
+        flat = self._sampler.engine.diag_energies(ham, np.concatenate(keys)) if keys else np.zeros(0)
+        out, pos = [], 0
+        for dist, k in zip(dists, keys):
+            out.append(float(ex.expectation_with_operator(dist, self._z_masks, self._coeffs, self._alpha, energies=flat[pos : pos + k.size])))
+            pos += k.size
         return out
 
     @property

@@ -49,11 +49,17 @@ def diagonal_energies(states: np.ndarray, z_masks: np.ndarray, coeffs: np.ndarra
     """E(k) = sum_j c_j (-1)^{popcount(k & z_j)} for every k in ``states`` (uint64), vectorised."""
     states = np.asarray(states, dtype=np.uint64).reshape(-1, 1)
     z = np.asarray(z_masks, dtype=np.uint64).reshape(1, -1)
-    v = states & z
-    for s in (32, 16, 8, 4, 2, 1):
-        v ^= v >> np.uint64(s)
-    sign = 1.0 - 2.0 * (v & np.uint64(1)).astype(np.float64)
-    return sign @ np.asarray(coeffs, dtype=np.float64)
+    odd = (np.bitwise_count(states & z) & 1).astype(np.float64)
+    return (1.0 - 2.0 * odd) @ np.asarray(coeffs, dtype=np.float64)
+
+
+def merge_diagonal_terms(z_masks: np.ndarray, coeffs: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """Sum the coefficients of repeated z-masks (the JSSP encoder emits 346 raw terms for 84 distinct masks at 26
+    qubits: SURVEY.md section 8a); first-appearance order is kept."""
+    order: dict = {}
+    for z, c in zip(np.asarray(z_masks, dtype=np.uint64).tolist(), np.asarray(coeffs, dtype=np.float64).tolist()):
+        order[z] = order.get(z, 0.0) + c
+    return np.fromiter(order.keys(), dtype=np.uint64, count=len(order)), np.fromiter(order.values(), dtype=np.float64, count=len(order))
 
 
 def expectation_with_operator(

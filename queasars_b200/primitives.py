@@ -114,13 +114,13 @@ class _B200Primitive:
                 self._queue_obj = CoalescingQueue(self._execute)
             return self._queue_obj
 
-    def hamiltonian_for(self, operator) -> HamiltonianHandle:
-        key = id(operator)
+    def hamiltonian_for(self, operator, build_table=None) -> HamiltonianHandle:
+        key = (id(operator), build_table)
         with self._lock:
             hit = self._ham_cache.get(key)
             if hit is not None and hit[0] is operator:
                 return hit[1]
-        handle = self.engine.hamiltonian(operator)
+        handle = self.engine.hamiltonian(operator, build_table=build_table)
         with self._lock:
             if len(self._ham_cache) > 64:
                 self._ham_cache.clear()
