@@ -91,6 +91,9 @@ class SamplerPubResult(PubResult):
 
 
 class PrimitiveResult:
+    def __class_getitem__(cls, item):  # upstream is Generic[T]; annotations like PrimitiveResult[PubResult] must work
+        return cls
+
     def __init__(self, pub_results: Iterable[PubResult], metadata: Optional[dict] = None):
         self._pub_results = list(pub_results)
         self.metadata = metadata or {}
@@ -106,6 +109,9 @@ class PrimitiveResult:
 
 
 class BasePrimitiveJob(ABC):
+    def __class_getitem__(cls, item):  # upstream is Generic[ResultT, StatusT]
+        return cls
+
     @abstractmethod
     def result(self):
         ...

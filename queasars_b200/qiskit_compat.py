@@ -17,13 +17,17 @@ import threading
 import types
 from abc import ABC, abstractmethod
 from concurrent.futures import Future, wait as _futures_wait
-from typing import Any, Optional, Union
+from typing import Any, Dict, List, Optional, TypeVar, Union
 
 import numpy as np
 
 from . import circuit as _circuit
 from . import containers as _containers
 from . import operators as _operators
+
+
+_T = TypeVar("_T")
+ListOrDict = Union[List[Optional[_T]], Dict[str, _T]]  # qiskit_algorithms.list_or_dict.ListOrDict
 
 
 def _missing(name: str) -> bool:
@@ -264,7 +268,7 @@ def install(force: bool = False) -> list[str]:
             NFT=_opt.NFT,
         )
         _module("qiskit_algorithms.utils", algorithm_globals=algorithm_globals)
-        _module("qiskit_algorithms.list_or_dict", ListOrDict=Union[list, dict])
+        _module("qiskit_algorithms.list_or_dict", ListOrDict=ListOrDict)
         installed.append("qiskit_algorithms")
     if force or _missing("dask"):
         _module("dask")
