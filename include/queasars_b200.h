@@ -50,7 +50,7 @@ extern "C" {
 typedef struct qb_sweep {
     int32_t tile_qubits[16]; /* first tile_bits entries used, ascending; tile-local bit i <-> this qubit */
     int32_t pass_begin, pass_end;
-    int32_t reserved[2];
+    int32_t op_begin, op_end; /* pass-op range of the whole sweep = [passes[pass_begin].op_begin, passes[pass_end-1].op_end) */
 } qb_sweep;
 
 typedef struct qb_pass {

@@ -84,7 +84,7 @@ struct HostBuf {  // pinned staging
 };
 
 struct Plan {
-    int n_qubits = 0, n_eff = 0, dtype = 0, tile_bits = QB_TILE_BITS, reg_bits = 4, n_params = 0, n_ops = 0, n_sweeps = 0;
+    int n_qubits = 0, n_eff = 0, dtype = 0, tile_bits = QB_TILE_BITS, reg_bits = 4, n_params = 0, n_ops = 0, n_sweeps = 0, n_pass_ops = 0;
     DevBuf sweeps, passes, pass_ops, angles, init_ops;
     bool has_init = false;
     ~Plan() { sweeps.release(), passes.release(), pass_ops.release(), angles.release(), init_ops.release(); }
@@ -233,7 +233,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
     b.n_state_sweeps = 0;
     for (int i = 0; i < batch; ++i) {
         b.param_begin[i + 1] = b.param_begin[i] + plans[i]->n_params;
-        op_begin[i + 1] = op_begin[i] + plans[i]->n_ops;
+        op_begin[i + 1] = op_begin[i] + plans[i]->n_ops + plans[i]->n_pass_ops;
         for (int s = 0; s < plans[i]->n_sweeps; ++s) b.active[s]++;
         b.n_state_sweeps += plans[i]->n_sweeps;
     }
@@ -274,6 +274,8 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         en.partials = b.partials.as<double>() + b.partial_stride * size_t(pos);
         en.n_sweeps = pl->n_sweeps;
         en.n_ops = pl->n_ops;
+        en.n_pass_ops = pl->n_pass_ops;
+        en.pad = 0;
         en.n_params = pl->n_params;
         en.init_zero = init_zero;
         en.index_offset = index_offset;
@@ -566,6 +568,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
             mask |= 1ull << q;
         }
         const int ob = passes[sw.pass_begin].op_begin, oe = passes[sw.pass_end - 1].op_end;
+        if (sw.op_begin != ob || sw.op_end != oe) return fail(QB_ERR_INVALID, "sweep op range does not match its passes");
         if (ob < 0 || oe > n_pass_ops || oe < ob || oe - ob > qb::kMaxSweepOps)
             return fail(QB_ERR_INVALID, "sweep " + std::to_string(s) + ": bad op range / too many ops");
         for (int p = sw.pass_begin; p < sw.pass_end; ++p) {
@@ -628,7 +631,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     std::lock_guard<std::mutex> lock(ctx->mu);
     QB_TRY(set_device(ctx));
     auto pl = std::make_unique<Plan>();
-    pl->n_qubits = n_qubits, pl->n_eff = n_eff, pl->dtype = dtype, pl->tile_bits = tile_bits, pl->reg_bits = reg_bits, pl->n_params = n_params, pl->n_ops = n_ops, pl->n_sweeps = n_sweeps;
+    pl->n_qubits = n_qubits, pl->n_eff = n_eff, pl->dtype = dtype, pl->tile_bits = tile_bits, pl->reg_bits = reg_bits, pl->n_params = n_params, pl->n_ops = n_ops, pl->n_sweeps = n_sweeps, pl->n_pass_ops = n_pass_ops;
     QB_TRY(upload(ctx, pl->sweeps, sweeps, sizeof(qb_sweep) * size_t(n_sweeps)));
     QB_TRY(upload(ctx, pl->passes, passes, sizeof(qb_pass) * size_t(n_passes)));
     QB_TRY(upload(ctx, pl->pass_ops, pass_ops, sizeof(qb_pass_op) * size_t(n_pass_ops)));

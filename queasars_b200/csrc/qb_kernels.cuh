@@ -39,11 +39,12 @@ struct BatchEntry {
     const qb_op_angles* angles;
     const int32_t* init_ops;   // device, n_eff entries (product-state start) or nullptr
     const double* params;      // device, n_params
-    double* matrices;          // device, n_ops * 8 (bound 2x2 complex matrices, row-major re/im)
+    double* matrices;          // device, (n_ops + n_pass_ops) * 8: bound 2x2 matrices by op index, then again in pass-op order
     void* state;               // device, 2^n_eff amplitudes
     const double* diag_table;  // device, 2^n_eff doubles, or nullptr
     double* partials;          // device, one double per tile (fused expectation epilogue)
     int32_t n_sweeps, n_ops, n_params, init_zero;
+    int32_t n_pass_ops, pad;
     uint64_t index_offset;
 };
 
@@ -207,27 +208,10 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
     __syncthreads();
     const int pass_begin = s_sweep.pass_begin;
     const int n_pass = s_sweep.pass_end - pass_begin;
-    for (int i = tid; i < n_pass * int(sizeof(qb_pass) / 4); i += kThreads)
-        reinterpret_cast<int32_t*>(s_pass)[i] = reinterpret_cast<const int32_t*>(en.passes + pass_begin)[i];
-    __syncthreads();
-    const int op_begin = s_pass[0].op_begin;
-    const int n_sop = s_pass[n_pass - 1].op_end - op_begin;
-    for (int i = tid; i < n_sop * int(sizeof(qb_pass_op) / 4); i += kThreads)
-        reinterpret_cast<int32_t*>(s_ops)[i] = reinterpret_cast<const int32_t*>(en.pass_ops + op_begin)[i];
-    __syncthreads();
-    {
-        T* s_mat_t = reinterpret_cast<T*>(s_mat);
-        const double* __restrict__ mats = en.matrices;
-        for (int i = tid; i < n_sop * 8; i += kThreads)
-            s_mat_t[i] = static_cast<T>(mats[size_t(s_ops[i >> 3].op_index) * 8 + (i & 7)]);
-        // pre-decoded dispatch words: variant | ctrl_qubit << 8 | tgt_qubit << 16
-        for (int i = tid; i <= n_sop; i += kThreads)
-            s_word[i] = (i < n_sop) ? (uint32_t(s_ops[i].variant) | (uint32_t(s_ops[i].ctrl_qubit) << 8) | (uint32_t(s_ops[i].tgt_qubit) << 16)) : 0u;
-    }
+    const int op_begin = s_sweep.op_begin;
+    const int n_sop = s_sweep.op_end - op_begin;
 
-    __syncthreads();  // matrices and dispatch words are staged
-    // tile base index = blockIdx.x scattered over the qubits that are not tile bits (every thread, redundantly: cheaper
-    // than serialising it behind a barrier)
+    // tile base index = blockIdx.x scattered over the qubits that are not tile bits
     uint64_t base = 0;
     {
         uint64_t tile_mask = 0;
@@ -245,13 +229,12 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
     const bool do_expect = fuse_expectation && (sweep_idx == en.n_sweeps - 1) && (en.diag_table != nullptr);
     const double* __restrict__ table = en.diag_table;
 
-    C a[kNReg];
-    for (int p = 0; p < n_pass; ++p) {
-        const qb_pass& ps = s_pass[p];
-        const bool first = (p == 0), last = (p == n_pass - 1);
-        // thread part of the tile-local index and the global offset it maps to
-        uint32_t e_thr = 0;
-        uint64_t g_thr = 0;
+    // Per-pass thread context: where this thread's 2^R amplitudes live in the tile / in global memory.
+    uint32_t e_thr, s_thr, so[kRegBits];
+    uint64_t g_thr, g0, go[kRegBits];
+    Idx i0, gi[kRegBits];
+    auto setup_pass = [&](const qb_pass& ps) {
+        e_thr = 0, g_thr = 0;
 #pragma unroll
         for (int b = 0; b < kThreadBits; ++b) {
             const uint32_t bit = (tid >> b) & 1u;
@@ -259,79 +242,109 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             e_thr |= bit << pos;
             g_thr |= uint64_t(bit) << s_sweep.tile_qubits[pos];
         }
-        const uint32_t s_thr = swz(e_thr);
-        uint32_t so[kRegBits];
-        uint64_t go[kRegBits];
-        Idx gi[kRegBits];
+        s_thr = swz(e_thr);
 #pragma unroll
         for (int i = 0; i < kRegBits; ++i) {
             so[i] = swz(1u << ps.reg_bits[i]);
             go[i] = 1ull << s_sweep.tile_qubits[ps.reg_bits[i]];
             gi[i] = Idx(go[i]);
         }
-        const uint64_t g0 = base | g_thr;
-        const Idx i0 = Idx(g0);
+        g0 = base | g_thr;
+        i0 = Idx(g0);
+    };
 
-        // ---- load ----
-        if (first) {
-            if (sweep_idx == 0 && en.init_zero && en.init_ops != nullptr) {
-                // product-state start: amplitude(k) = prod_q v_q[bit_q(k)], v_q = first column of qubit q's first
-                // gate (or |0>).  P collects the factors of all index bits shared by this thread's amplitudes, the
-                // register bits are expanded by doubling.
-                const uint64_t Wi = gbase | g_thr;
-                uint64_t reg_qubits = 0;
+    // ---- first pass: its record comes straight from global memory so that the HBM loads of the tile are in flight
+    //      while the rest of the sweep program (passes, ops, matrices) is staged into shared memory
+    C a[kNReg];
+    {
+        const qb_pass ps = en.passes[pass_begin];
+        setup_pass(ps);
+        if (sweep_idx == 0 && en.init_zero && en.init_ops != nullptr) {
+            // product-state start: amplitude(k) = prod_q v_q[bit_q(k)], v_q = first column of qubit q's first
+            // gate (or |0>).  P collects the factors of all index bits shared by this thread's amplitudes, the
+            // register bits are expanded by doubling.
+            const uint64_t Wi = gbase | g_thr;
+            uint64_t reg_qubits = 0;
 #pragma unroll
-                for (int i = 0; i < kRegBits; ++i) reg_qubits |= go[i];
-                const int32_t* __restrict__ init_ops = en.init_ops;
-                const double* __restrict__ mats = en.matrices;
-                C P;
-                P.x = T(1), P.y = T(0);
-                for (int q = 0; q < n_eff; ++q) {
-                    if ((reg_qubits >> q) & 1ull) continue;
-                    const int op = init_ops[q];
-                    const bool one = (Wi >> q) & 1ull;
-                    if (op < 0) {
-                        if (one) P.x = T(0), P.y = T(0);
-                    } else {
-                        const double* m = mats + size_t(op) * 8 + (one ? 4 : 0);
-                        C v;
-                        v.x = T(m[0]), v.y = T(m[1]);
-                        P = cmul<T>(P, v);
-                    }
-                }
-                if ((en.index_offset >> n_eff) != 0) P.x = T(0), P.y = T(0);  // rank bits above the local register start in |0>
-                a[0] = P;
-#pragma unroll
-                for (int i = 0; i < kRegBits; ++i) {
-                    const int q = s_sweep.tile_qubits[ps.reg_bits[i]];
-                    const int op = init_ops[q];
-                    C v0, v1;
-                    v0.x = T(1), v0.y = T(0), v1.x = T(0), v1.y = T(0);
-                    if (op >= 0) {
-                        const double* m = mats + size_t(op) * 8;
-                        v0.x = T(m[0]), v0.y = T(m[1]), v1.x = T(m[4]), v1.y = T(m[5]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < (1 << i); ++j) {
-                        a[j | (1 << i)] = cmul<T>(a[j], v1);
-                        a[j] = cmul<T>(a[j], v0);
-                    }
-                }
-            } else if (sweep_idx == 0 && en.init_zero) {
-#pragma unroll
-                for (int j = 0; j < kNReg; ++j) {
-                    const uint64_t idx = g0 | reg_offset<kRegBits>(j, go);
-                    a[j].x = ((idx | en.index_offset) == 0) ? T(1) : T(0);
-                    a[j].y = T(0);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < kNReg; ++j) {
-                    const Idx idx = i0 | reg_offset<kRegBits>(j, gi);
-                    a[j] = ld_state(st + idx);
+            for (int i = 0; i < kRegBits; ++i) reg_qubits |= go[i];
+            const int32_t* __restrict__ init_ops = en.init_ops;
+            const double* __restrict__ mats = en.matrices;
+            C P;
+            P.x = T(1), P.y = T(0);
+            for (int q = 0; q < n_eff; ++q) {
+                if ((reg_qubits >> q) & 1ull) continue;
+                const int op = init_ops[q];
+                const bool one = (Wi >> q) & 1ull;
+                if (op < 0) {
+                    if (one) P.x = T(0), P.y = T(0);
+                } else {
+                    const double* m = mats + size_t(op) * 8 + (one ? 4 : 0);
+                    C v;
+                    v.x = T(m[0]), v.y = T(m[1]);
+                    P = cmul<T>(P, v);
                 }
             }
+            if ((en.index_offset >> n_eff) != 0) P.x = T(0), P.y = T(0);  // rank bits above the local register start in |0>
+            a[0] = P;
+#pragma unroll
+            for (int i = 0; i < kRegBits; ++i) {
+                const int q = s_sweep.tile_qubits[ps.reg_bits[i]];
+                const int op = init_ops[q];
+                C v0, v1;
+                v0.x = T(1), v0.y = T(0), v1.x = T(0), v1.y = T(0);
+                if (op >= 0) {
+                    const double* m = mats + size_t(op) * 8;
+                    v0.x = T(m[0]), v0.y = T(m[1]), v1.x = T(m[4]), v1.y = T(m[5]);
+                }
+#pragma unroll
+                for (int j = 0; j < (1 << i); ++j) {
+                    a[j | (1 << i)] = cmul<T>(a[j], v1);
+                    a[j] = cmul<T>(a[j], v0);
+                }
+            }
+        } else if (sweep_idx == 0 && en.init_zero) {
+#pragma unroll
+            for (int j = 0; j < kNReg; ++j) {
+                const uint64_t idx = g0 | reg_offset<kRegBits>(j, go);
+                a[j].x = ((idx | en.index_offset) == 0) ? T(1) : T(0);
+                a[j].y = T(0);
+            }
         } else {
+#pragma unroll
+            for (int j = 0; j < kNReg; ++j) {
+                const Idx idx = i0 | reg_offset<kRegBits>(j, gi);
+                a[j] = ld_state(st + idx);
+            }
+        }
+    }
+
+    // ---- stage the sweep program: all four copies are independent (ranges come from the sweep record, matrices are
+    //      stored in pass-op order by bind_kernel), one barrier publishes them
+    for (int i = tid; i < n_pass * int(sizeof(qb_pass) / 4); i += kThreads)
+        reinterpret_cast<int32_t*>(s_pass)[i] = reinterpret_cast<const int32_t*>(en.passes + pass_begin)[i];
+    for (int i = tid; i < n_sop * int(sizeof(qb_pass_op) / 4); i += kThreads)
+        reinterpret_cast<int32_t*>(s_ops)[i] = reinterpret_cast<const int32_t*>(en.pass_ops + op_begin)[i];
+    {
+        T* s_mat_t = reinterpret_cast<T*>(s_mat);
+        const double* __restrict__ mats = en.matrices + (size_t(en.n_ops) + size_t(op_begin)) * 8;
+        for (int i = tid; i < n_sop * 8; i += kThreads) s_mat_t[i] = static_cast<T>(mats[i]);
+        // pre-decoded dispatch words: variant | ctrl_qubit << 8 | tgt_qubit << 16
+        for (int i = tid; i <= n_sop; i += kThreads) {
+            uint32_t w = 0;
+            if (i < n_sop) {
+                const qb_pass_op po = en.pass_ops[op_begin + i];
+                w = uint32_t(po.variant) | (uint32_t(po.ctrl_qubit) << 8) | (uint32_t(po.tgt_qubit) << 16);
+            }
+            s_word[i] = w;
+        }
+    }
+    __syncthreads();
+
+    for (int p = 0; p < n_pass; ++p) {
+        const qb_pass& ps = s_pass[p];
+        const bool first = (p == 0), last = (p == n_pass - 1);
+        if (!first) {
+            setup_pass(ps);
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
                 const uint32_t si = s_thr ^ reg_offset<kRegBits>(j, so);
@@ -425,34 +438,38 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
 // ---------------------------------------------------------------------------------------------------
 // parameter binding: grid = batch entries
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bind_matrix(const qb_op_angles& ang, const double* __restrict__ params, double* __restrict__ m) {
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ang.cnst[j] + (ang.slot[j] >= 0 ? ang.coeff[j] * params[ang.slot[j]] : 0.0);
+    const double g = v[0], t = v[1], p = v[2], l = v[3];
+    double s, c;
+    if (ang.kind == QB_OP_DIAG) {
+        sincos(g, &s, &c);
+        m[0] = c, m[1] = s, m[2] = 0.0, m[3] = 0.0, m[4] = 0.0, m[5] = 0.0;
+        sincos(g + l, &s, &c);
+        m[6] = c, m[7] = s;
+    } else {
+        double sh, ch;
+        sincos(0.5 * t, &sh, &ch);
+        sincos(g, &s, &c);
+        m[0] = c * ch, m[1] = s * ch;
+        sincos(g + l, &s, &c);
+        m[2] = -c * sh, m[3] = -s * sh;
+        sincos(g + p, &s, &c);
+        m[4] = c * sh, m[5] = s * sh;
+        sincos(g + p + l, &s, &c);
+        m[6] = c * ch, m[7] = s * ch;
+    }
+}
+
+// matrices[0 .. n_ops) by op index (read by the product-state start), matrices[n_ops .. n_ops + n_pass_ops) in pass-op
+// order (what a sweep stages: one contiguous, index-free copy)
 __global__ void bind_kernel(const BatchEntry* __restrict__ entries) {
     const BatchEntry& en = entries[blockIdx.x];
-    for (int o = threadIdx.x; o < en.n_ops; o += blockDim.x) {
-        const qb_op_angles& ang = en.angles[o];
-        double v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = ang.cnst[j] + (ang.slot[j] >= 0 ? ang.coeff[j] * en.params[ang.slot[j]] : 0.0);
-        const double g = v[0], t = v[1], p = v[2], l = v[3];
-        double* m = en.matrices + size_t(o) * 8;
-        double s, c;
-        if (ang.kind == QB_OP_DIAG) {
-            sincos(g, &s, &c);
-            m[0] = c, m[1] = s, m[2] = 0.0, m[3] = 0.0, m[4] = 0.0, m[5] = 0.0;
-            sincos(g + l, &s, &c);
-            m[6] = c, m[7] = s;
-        } else {
-            double sh, ch;
-            sincos(0.5 * t, &sh, &ch);
-            sincos(g, &s, &c);
-            m[0] = c * ch, m[1] = s * ch;
-            sincos(g + l, &s, &c);
-            m[2] = -c * sh, m[3] = -s * sh;
-            sincos(g + p, &s, &c);
-            m[4] = c * sh, m[5] = s * sh;
-            sincos(g + p + l, &s, &c);
-            m[6] = c * ch, m[7] = s * ch;
-        }
-    }
+    for (int o = threadIdx.x; o < en.n_ops; o += blockDim.x) bind_matrix(en.angles[o], en.params, en.matrices + size_t(o) * 8);
+    for (int i = threadIdx.x; i < en.n_pass_ops; i += blockDim.x)
+        bind_matrix(en.angles[en.pass_ops[i].op_index], en.params, en.matrices + (size_t(en.n_ops) + size_t(i)) * 8);
 }
 
 // ---------------------------------------------------------------------------------------------------

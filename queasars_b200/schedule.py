@@ -274,7 +274,7 @@ def plan_circuit(
 # -------------------------------------------------------------------------------------------------
 # flat encoding handed to the C-ABI (layout documented in include/queasars_b200.h)
 # -------------------------------------------------------------------------------------------------
-SWEEP_DTYPE = np.dtype([("tile_qubits", np.int32, (16,)), ("pass_begin", np.int32), ("pass_end", np.int32), ("reserved", np.int32, (2,))], align=True)
+SWEEP_DTYPE = np.dtype([("tile_qubits", np.int32, (16,)), ("pass_begin", np.int32), ("pass_end", np.int32), ("op_begin", np.int32), ("op_end", np.int32)], align=True)
 PASS_DTYPE = np.dtype([("reg_bits", np.int32, (4,)), ("op_begin", np.int32), ("op_end", np.int32), ("thread_bits", np.uint8, (12,))], align=True)
 PASSOP_DTYPE = np.dtype(
     [("op_index", np.int32), ("kind", np.uint8), ("tgt_kind", np.uint8), ("tgt_pos", np.uint8), ("ctrl_kind", np.uint8), ("ctrl_pos", np.uint8), ("variant", np.uint8), ("ctrl_qubit", np.uint8), ("tgt_qubit", np.uint8)],
@@ -313,6 +313,7 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
     for si, sw in enumerate(plan.sweeps):
         sweeps[si]["tile_qubits"][: len(sw.tile_qubits)] = sw.tile_qubits
         sweeps[si]["pass_begin"] = pi
+        sweeps[si]["op_begin"] = oi
         for ps in sw.passes:
             passes[pi]["reg_bits"][: len(ps.reg_bits)] = ps.reg_bits
             passes[pi]["thread_bits"][: len(ps.thread_bits)] = ps.thread_bits
@@ -327,6 +328,7 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
             passes[pi]["op_end"] = oi
             pi += 1
         sweeps[si]["pass_end"] = pi
+        sweeps[si]["op_end"] = oi
     angles = np.zeros(max(1, len(ops)), dtype=ANGLE_DTYPE)
     for i, op in enumerate(ops):
         for j, a in enumerate(op.angles):
