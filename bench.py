@@ -45,6 +45,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per sweep launch of this workload, from the committed ncu --set full
+    capture (profiles/r1_sweep20_traffic.json); None when no capture is present."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_sweep20_traffic.json")) as fh:
+            return float(json.load(fh)["mean_traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     QUERY = (
         "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -294,7 +304,8 @@ def run_b200(args):
         "peak_kind": peak_kind,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": None,
+        "traffic": profiled_traffic(),
+        "algorithmic_bytes_per_launch": sweep_bytes * tot_states / max(1, 3 * stats["sweep_launches"]),
         "bytes_per_statevector_sweep": sweep_bytes,
         "sweeps_per_evaluation": stats["state_sweeps"] / POPULATION,
         "gates_per_sweep": float(np.mean([p.n_ops for p in plans])) / (stats["state_sweeps"] / POPULATION),
@@ -332,36 +343,51 @@ def run_b200(args):
 
 
 def gate_apply_probe(engine, estimator, peak, args):
-    """Sweep kernel on one HBM-resident 26-qubit state (1 GiB): achieved GB/s per sweep launch."""
+    """The sweep kernel on ONE HBM-resident state of 26 / 28 / 30 qubits (1 / 4 / 16 GiB), two regimes:
+      fused_evqe   a random EVQE individual: ~17 gates fused per sweep -> FP64-issue bound by design
+      hbm_regime   layers of 7 ``u`` gates on 7 non-low qubits: one read+write sweep per layer -> HBM bound
+    GB/s = algorithmic sweep bytes (2 * 16 B * 2^n) / CUDA-event time of each read+write sweep launch; the first sweep
+    of a circuit (product-state start, write only) is excluded."""
+    from queasars_b200 import gate_list as gl
     from queasars_b200 import genome as gn
+    from queasars_b200.circuit import QuantumCircuit
 
-    out = {}
-    for n, layers in ((26, args.layers), (28, 2)):
-        ind = gn.Individual.random(n, layers, True, 7)
-        plan = engine.compile(__import__("queasars_b200.gate_list", fromlist=["x"]).from_evqe_individual(ind))
-        ham = engine.hamiltonian(gn.ising_operator(n), build_table=True) if n <= 26 else None
-        rb = engine.resident_batch([plan], ham)
-        rb.set_params([list(ind.parameter_values)])
-        for _ in range(3):
+    def measure(plan, params, reps):
+        rb = engine.resident_batch([plan], None)
+        rb.set_params([params])
+        for _ in range(2):
             rb.run()
         tot_ms, launches = 0.0, 0
-        for _ in range(5):
-            ms, states = rb.run_timed()
-            tot_ms += float(ms.sum())
-            launches += len(ms)
+        for _ in range(reps):
+            ms, _states = rb.run_timed()
+            tot_ms += float(ms[1:].sum())
+            launches += len(ms) - 1
         bytes_per = rb.stats()["sweep_bytes"]
-        gbs = bytes_per * launches / (tot_ms * 1e-3) / 1e9
-        out[f"{n}q"] = {
-            "layers": layers,
-            "gates": plan.n_ops,
-            "sweeps": plan.n_sweeps,
-            "gates_per_sweep": plan.n_ops / plan.n_sweeps,
-            "ms_per_sweep": tot_ms / launches,
-            "GBps": gbs,
-            "frac_of_measured_hbm": gbs / peak,
-            "evals_per_s": 1e3 / (tot_ms / 5),
-        }
         rb.close()
+        gbs = bytes_per * launches / (tot_ms * 1e-3) / 1e9 if launches else None
+        return {"sweeps_rw": launches // reps, "ms_per_sweep": tot_ms / max(1, launches), "GBps": gbs, "frac_of_measured_hbm": gbs / peak if gbs else None}
+
+    out = {}
+    for n, layers in ((26, args.layers), (28, 4), (30, 4)):
+        ind = gn.Individual.random(n, layers, True, 7)
+        plan = engine.compile(gl.from_evqe_individual(ind))
+        fused = measure(plan, list(ind.parameter_values), 3)
+        n_u = sum(1 for layer in ind.layers for g in layer.gates if type(g).__name__ == "Rotation")
+        n_cu3 = sum(1 for layer in ind.layers for g in layer.gates if type(g).__name__ == "ControlledRotation")
+        fused.update(layers=layers, gates=plan.n_ops, gates_per_sweep=plan.n_ops / plan.n_sweeps)
+        # what the same gates would move if applied one sweep per gate (SURVEY.md 8d "effective GB/s")
+        total_ms = fused["ms_per_sweep"] * fused["sweeps_rw"]
+        fused["effective_unfused_GBps"] = (2 * n_u + n_cu3) * 16 * (1 << n) / (total_ms * 1e-3) / 1e9 if total_ms else None
+        circ = QuantumCircuit(n)
+        for q in range(n):
+            circ.u(0.1 + 0.01 * q, 0.2, 0.3, q)  # absorbed into the product-state start
+        for layer in range(3):
+            for g in range(7):
+                circ.u(0.3 + g, 0.2 * layer, 0.1, 4 + ((g * 3 + 7 * layer) % (n - 4)))
+        plan = engine.compile(gl.from_circuit(circ))
+        hbm = measure(plan, [], 3)
+        hbm.update(gates_per_sweep=21 / max(1, plan.n_sweeps - 1))
+        out[f"{n}q"] = {"fused_evqe": fused, "hbm_regime": hbm}
     return out
 
 
