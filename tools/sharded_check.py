@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--qubits", dest="n", type=int, default=26)
 ap.add_argument("--layers", type=int, default=2)
 ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--analytic", type=int, default=0, help="product-state circuit with analytically known <Z_q>, <Z_p Z_q>")
 args = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -28,13 +29,32 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-ind = gn.Individual.random(args.n, args.layers, True, 11)
-gates = gl.from_evqe_individual(ind)
 op = gn.ising_operator(args.n, seed=3)
 _, z, c = op.masks()
 z, c = z[: 2 * args.n], c.real[: 2 * args.n]  # n Z terms + n ZZ terms keep the on-the-fly diagonal kernel cheap
+analytic_value = None
+if args.analytic:
+    from queasars_b200.circuit import QuantumCircuit
+
+    thetas = np.random.default_rng(5).uniform(0, np.pi, args.n)
+    circ = QuantumCircuit(args.n)
+    for rep in range(2):  # two half rotations per qubit: the second one is a real gate on an existing state
+        for q in range(args.n):
+            circ.ry(float(thetas[q]) / 2, q)
+    gates = gl.from_circuit(circ)
+    cosines = np.cos(thetas)
+    analytic_value = float(sum(cf * np.prod([cosines[q] for q in range(args.n) if (int(zm) >> q) & 1]) for zm, cf in zip(z, c)))
+
+    class _Ind:
+        parameter_values = ()
+
+    ind = _Ind()
+else:
+    ind = gn.Individual.random(args.n, args.layers, True, 11)
+    gates = gl.from_evqe_individual(ind)
 
 sv = ShardedStatevector(args.n)
+swaps_in_run = None
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -42,6 +62,7 @@ t0 = time.perf_counter()
 sv.run(gates, ind.parameter_values)
 torch.cuda.synchronize()
 t_run = time.perf_counter() - t0
+swaps_in_run = sv.swaps_done
 t0 = time.perf_counter()
 value = sv.diagonal_expectation(z, c)
 t_exp = time.perf_counter() - t0
@@ -62,7 +83,8 @@ if world > 1:
     swap_ms = e0.elapsed_time(e1) / 4
 
 if rank == 0:
-    out = {"n": args.n, "world": world, "n_local": sv.n_local, "gates": len(gates.ops), "swaps": sv.swaps_done, "value": value,
+    out = {"n": args.n, "world": world, "n_local": sv.n_local, "gates": len(gates.ops), "swaps": swaps_in_run, "value": value, "analytic_value": analytic_value,
+           "analytic_rel_err": None if analytic_value is None else abs(value - analytic_value) / max(1.0, abs(analytic_value)),
            "norm_err": abs(norm - 1.0), "run_s": t_run, "expectation_s": t_exp}
     if swap_ms is not None:
         shard_bytes = 16 * (1 << sv.n_local)
