@@ -261,47 +261,44 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
         setup_pass(ps);
         if (sweep_idx == 0 && en.init_zero && en.init_ops != nullptr) {
             // product-state start: amplitude(k) = prod_q v_q[bit_q(k)], v_q = first column of qubit q's first
-            // gate (or |0>).  P collects the factors of all index bits shared by this thread's amplitudes, the
-            // register bits are expanded by doubling.
+            // gate (or |0>).  The 2 * n_eff single-qubit amplitudes are staged in shared memory (reusing the tile
+            // buffer, which nothing has touched yet); P collects the factors of all index bits shared by this
+            // thread's amplitudes, the register bits are expanded by doubling.
+            C* s_init = tile;  // [q][0 | 1]
+            for (int i = tid; i < 2 * n_eff; i += kThreads) {
+                const int op = en.init_ops[i >> 1];
+                C v;
+                v.x = (i & 1) ? T(0) : T(1), v.y = T(0);
+                if (op >= 0) {
+                    const double* m = en.matrices + size_t(op) * 8 + ((i & 1) ? 4 : 0);
+                    v.x = T(m[0]), v.y = T(m[1]);
+                }
+                s_init[i] = v;
+            }
+            __syncthreads();
             const uint64_t Wi = gbase | g_thr;
             uint64_t reg_qubits = 0;
 #pragma unroll
             for (int i = 0; i < kRegBits; ++i) reg_qubits |= go[i];
-            const int32_t* __restrict__ init_ops = en.init_ops;
-            const double* __restrict__ mats = en.matrices;
             C P;
             P.x = T(1), P.y = T(0);
             for (int q = 0; q < n_eff; ++q) {
                 if ((reg_qubits >> q) & 1ull) continue;
-                const int op = init_ops[q];
-                const bool one = (Wi >> q) & 1ull;
-                if (op < 0) {
-                    if (one) P.x = T(0), P.y = T(0);
-                } else {
-                    const double* m = mats + size_t(op) * 8 + (one ? 4 : 0);
-                    C v;
-                    v.x = T(m[0]), v.y = T(m[1]);
-                    P = cmul<T>(P, v);
-                }
+                P = cmul<T>(P, s_init[2 * q + int((Wi >> q) & 1ull)]);
             }
             if ((en.index_offset >> n_eff) != 0) P.x = T(0), P.y = T(0);  // rank bits above the local register start in |0>
             a[0] = P;
 #pragma unroll
             for (int i = 0; i < kRegBits; ++i) {
                 const int q = s_sweep.tile_qubits[ps.reg_bits[i]];
-                const int op = init_ops[q];
-                C v0, v1;
-                v0.x = T(1), v0.y = T(0), v1.x = T(0), v1.y = T(0);
-                if (op >= 0) {
-                    const double* m = mats + size_t(op) * 8;
-                    v0.x = T(m[0]), v0.y = T(m[1]), v1.x = T(m[4]), v1.y = T(m[5]);
-                }
+                const C v0 = s_init[2 * q], v1 = s_init[2 * q + 1];
 #pragma unroll
                 for (int j = 0; j < (1 << i); ++j) {
                     a[j | (1 << i)] = cmul<T>(a[j], v1);
                     a[j] = cmul<T>(a[j], v0);
                 }
             }
+            __syncthreads();  // s_init aliases the tile buffer: everyone is done reading before a pass may overwrite it
         } else if (sweep_idx == 0 && en.init_zero) {
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {

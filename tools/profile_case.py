@@ -16,12 +16,24 @@ ap.add_argument("--layers", type=int, default=6)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--runs", type=int, default=3)
 ap.add_argument("--dtype", default="complex128")
+ap.add_argument("--oploop", type=int, default=0, help="op-loop probe: u on every qubit (absorbed), then this many layers of u on the 4 highest qubits (one pass)")
 ap.add_argument("--simple", type=int, default=0, help="instead of an EVQE genome: this many u gates on distinct high qubits, repeated --layers times")
 args = ap.parse_args()
 
 engine = Engine(0, args.dtype)
 inds = gn.random_population(args.n, args.layers, args.batch, True, 7)
-if args.simple:
+if args.oploop:
+    from queasars_b200.circuit import QuantumCircuit
+
+    circ = QuantumCircuit(args.n)
+    for q in range(args.n):
+        circ.u(0.1 + 0.01 * q, 0.2, 0.3, q)
+    for layer in range(args.oploop):
+        for g in range(4):
+            circ.u(0.3 + g, 0.2 * layer, 0.1, args.n - 1 - g)
+    plans = [engine.compile(gl.from_circuit(circ))] * args.batch
+    params = [[] for _ in range(args.batch)]
+elif args.simple:
     from queasars_b200.circuit import QuantumCircuit
 
     circ = QuantumCircuit(args.n)
