@@ -116,6 +116,12 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
  * sweep then synthesises the product state prod_q v_q[bit_q(k)] instead of |0...0>.  Such ops must not appear in
  * any pass. */
 int qb_plan_destroy(qb_context* ctx, int64_t plan_id);
+/* Prefix-state reuse (the optimizer loop of evqe/evolutionary_algorithm/mutation.py:57-81 re-evaluates
+ * ONE circuit whose leading layers are bound numerically and only one layer's parameters change): `plan_id` (compiled
+ * for application to an existing state, no parameters in the prefix) starts from the state produced by the
+ * parameter-free plan `prefix_plan_id` instead of |0...0>.  The prefix state is computed once, on first use, and kept on
+ * the device (16 B * 2^n) until the plan is destroyed. */
+int qb_plan_set_prefix(qb_context* ctx, int64_t plan_id, int64_t prefix_plan_id);
 
 /* --- Hamiltonians ---------------------------------------------------------------------------------------
  * H = sum_t (coeff_re[t] + i coeff_im[t]) * P_t with P_t = i^{popcount(x&z)} X^{x_mask} Z^{z_mask}

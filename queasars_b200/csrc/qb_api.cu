@@ -87,7 +87,10 @@ struct Plan {
     int n_qubits = 0, n_eff = 0, dtype = 0, tile_bits = QB_TILE_BITS, reg_bits = 4, n_params = 0, n_ops = 0, n_sweeps = 0, n_pass_ops = 0;
     DevBuf sweeps, passes, pass_ops, angles, init_ops;
     bool has_init = false;
-    ~Plan() { sweeps.release(), passes.release(), pass_ops.release(), angles.release(), init_ops.release(); }
+    int64_t prefix_id = 0;     // parameter-free plan whose result this plan starts from (0: none)
+    DevBuf prefix_state;       // cached result of the prefix plan
+    bool prefix_ready = false;
+    ~Plan() { sweeps.release(), passes.release(), pass_ops.release(), angles.release(), init_ops.release(), prefix_state.release(); }
 };
 
 struct Group {
@@ -195,6 +198,27 @@ Ham* find_ham(qb_context* ctx, int64_t id) {
     return it == ctx->hams.end() ? nullptr : it->second.get();
 }
 
+int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_ids, const Ham* ham, void* external_state,
+                int init_zero, uint64_t index_offset);
+int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events);
+
+// Compute (once) the state a prefixed plan starts from: run the parameter-free prefix plan into a buffer owned by the plan.
+int ensure_prefix_state(qb_context* ctx, Plan* pl) {
+    if (!pl->prefix_id || pl->prefix_ready) return QB_OK;
+    Plan* pre = find_plan(ctx, pl->prefix_id);
+    if (!pre) return fail(QB_ERR_NOT_FOUND, "prefix plan " + std::to_string(pl->prefix_id) + " no longer exists");
+    if (pre->n_eff != pl->n_eff || pre->dtype != pl->dtype || pre->n_params != 0 || pre->prefix_id)
+        return fail(QB_ERR_INVALID, "prefix plan must be parameter-free, un-prefixed and of the same shape");
+    const size_t state_bytes = (size_t(1) << pl->n_eff) * amp_bytes(pl->dtype);
+    QB_TRY(pl->prefix_state.reserve(state_bytes));
+    DeviceBatch tmp;
+    QB_TRY(build_batch(ctx, tmp, 1, &pl->prefix_id, nullptr, pl->prefix_state.p, 1, 0));
+    QB_TRY(launch_circuits(ctx, tmp, nullptr));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));  // tmp's small device buffers are released when it goes out of scope
+    pl->prefix_ready = true;
+    return QB_OK;
+}
+
 // ---- batch assembly -------------------------------------------------------------------------------
 int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_ids, const Ham* ham, void* external_state,
                 int init_zero, uint64_t index_offset) {
@@ -207,6 +231,10 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
             plans[i]->reg_bits != plans[0]->reg_bits || plans[i]->tile_bits != plans[0]->tile_bits)
             return fail(QB_ERR_INVALID, "all plans of one batch must share qubit count, dtype and tile / register-bit counts");
     }
+    for (int i = 0; i < batch; ++i)
+        if (plans[i]->prefix_id && (external_state || !init_zero))
+            return fail(QB_ERR_INVALID, "a plan with a cached prefix state cannot be applied to an external state");
+    for (int i = 0; i < batch; ++i) QB_TRY(ensure_prefix_state(ctx, plans[i]));
     if (!init_zero)
         for (int i = 0; i < batch; ++i)
             if (plans[i]->has_init) return fail(QB_ERR_INVALID, "plan was compiled for a |0...0> start (product-state prefix) but is applied to an existing state");
@@ -270,6 +298,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         en.params = b.params.as<double>() + b.param_begin[i];
         en.matrices = b.matrices.as<double>() + 8 * op_begin[i];
         en.state = static_cast<unsigned char*>(b.states.p) + state_bytes * size_t(pos);
+        en.src_state = pl->prefix_id ? pl->prefix_state.p : nullptr;
         en.diag_table = b.fuse_expect ? ham->table.as<double>() : nullptr;
         en.partials = b.partials.as<double>() + b.partial_stride * size_t(pos);
         en.n_sweeps = pl->n_sweeps;
@@ -277,7 +306,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         en.n_pass_ops = pl->n_pass_ops;
         en.pad = 0;
         en.n_params = pl->n_params;
-        en.init_zero = init_zero;
+        en.init_zero = pl->prefix_id ? 0 : init_zero;
         en.index_offset = index_offset;
     }
     {   // entries go through the pinned staging buffer so the copy is truly asynchronous
@@ -321,7 +350,7 @@ template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context
     return QB_OK;
 }
 
-int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events = nullptr) {
+int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     qb::bind_kernel<<<b.batch, 128, 0, ctx->stream>>>(b.entries.as<qb::BatchEntry>());
     QB_TRY(check_launch(ctx, "bind_kernel"));
     // amplitude indices fit 32 bits up to 31 local qubits: cheaper address arithmetic for the common sizes
@@ -644,6 +673,20 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     return QB_OK;
 }
 
+int qb_plan_set_prefix(qb_context* ctx, int64_t plan_id, int64_t prefix_plan_id) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    Plan* pl = find_plan(ctx, plan_id);
+    Plan* pre = find_plan(ctx, prefix_plan_id);
+    if (!pl || !pre) return fail(QB_ERR_NOT_FOUND, "unknown plan id");
+    if (pl->has_init) return fail(QB_ERR_INVALID, "a prefixed plan must be compiled for application to an existing state");
+    if (pre->n_params != 0 || pre->prefix_id || pre->n_eff != pl->n_eff || pre->dtype != pl->dtype || pre->n_qubits != pl->n_qubits)
+        return fail(QB_ERR_INVALID, "prefix plan must be parameter-free, un-prefixed and of the same shape");
+    pl->prefix_id = prefix_plan_id;
+    pl->prefix_ready = false;
+    return QB_OK;
+}
+
 int qb_plan_destroy(qb_context* ctx, int64_t plan_id) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -862,7 +905,7 @@ int qb_batch_run(qb_context* ctx, int64_t batch_id) {
     DeviceBatch* b = find_batch(ctx, batch_id);
     if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
     const int64_t before = ctx->launches;
-    QB_TRY(launch_circuits(ctx, *b));
+    QB_TRY(launch_circuits(ctx, *b, nullptr));
     if (b->ham) QB_TRY(launch_expectation(ctx, *b));
     b->launches_per_run = ctx->launches - before;
     return QB_OK;
@@ -940,7 +983,7 @@ int qb_evaluate_expectation(qb_context* ctx, int batch, const int64_t* plan_ids,
         DeviceBatch& b = ctx->oneshot;
         QB_TRY(build_batch(ctx, b, n, plan_ids + lo, ham, nullptr, 1, 0));
         QB_TRY(batch_upload_params(ctx, b, params, param_offsets + lo));
-        QB_TRY(launch_circuits(ctx, b));
+        QB_TRY(launch_circuits(ctx, b, nullptr));
         QB_TRY(launch_expectation(ctx, b));
         QB_TRY(batch_read(ctx, b, out_values + lo));
     }
@@ -961,7 +1004,7 @@ int qb_sample(qb_context* ctx, int batch, const int64_t* plan_ids, const double*
         DeviceBatch& b = ctx->oneshot;
         QB_TRY(build_batch(ctx, b, n, plan_ids + lo, nullptr, nullptr, 1, 0));
         QB_TRY(batch_upload_params(ctx, b, params, param_offsets + lo));
-        QB_TRY(launch_circuits(ctx, b));
+        QB_TRY(launch_circuits(ctx, b, nullptr));
         const uint64_t size = uint64_t(1) << b.n_eff;
         const uint64_t n_chunks = size >> qb::kChunkBits;
         const size_t u_bytes = sizeof(double) * size_t(n) * size_t(shots);
@@ -1016,7 +1059,7 @@ int qb_statevector(qb_context* ctx, int64_t plan_id, const double* params, int n
     QB_TRY(build_batch(ctx, b, 1, &plan_id, nullptr, nullptr, 1, 0));
     const int64_t offs[2] = {0, n_params};
     QB_TRY(batch_upload_params(ctx, b, params, offs));
-    QB_TRY(launch_circuits(ctx, b));
+    QB_TRY(launch_circuits(ctx, b, nullptr));
     const uint64_t size = uint64_t(1) << pl->n_qubits;
     const void* src = b.states.p;
     if (pl->dtype == QB_C64) {
@@ -1041,7 +1084,7 @@ int qb_apply_plan_device(qb_context* ctx, int64_t plan_id, const double* params_
     QB_TRY(build_batch(ctx, b, 1, &plan_id, nullptr, d_state, init_zero_state, index_offset));
     const int64_t offs[2] = {0, n_params};
     QB_TRY(batch_upload_params(ctx, b, params_host, offs));
-    QB_TRY(launch_circuits(ctx, b));
+    QB_TRY(launch_circuits(ctx, b, nullptr));
     QB_CUDA(cudaStreamSynchronize(ctx->stream));
     return QB_OK;
 }

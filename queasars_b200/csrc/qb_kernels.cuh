@@ -41,6 +41,7 @@ struct BatchEntry {
     const double* params;      // device, n_params
     double* matrices;          // device, (n_ops + n_pass_ops) * 8: bound 2x2 matrices by op index, then again in pass-op order
     void* state;               // device, 2^n_eff amplitudes
+    const void* src_state;     // optional: the first sweep reads this (cached prefix state) instead of `state`
     const double* diag_table;  // device, 2^n_eff doubles, or nullptr
     double* partials;          // device, one double per tile (fused expectation epilogue)
     int32_t n_sweeps, n_ops, n_params, init_zero;
@@ -307,10 +308,11 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                 a[j].y = T(0);
             }
         } else {
+            const C* __restrict__ src = (sweep_idx == 0 && en.src_state != nullptr) ? reinterpret_cast<const C*>(en.src_state) : st;
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
                 const Idx idx = i0 | reg_offset<kRegBits>(j, gi);
-                a[j] = ld_state(st + idx);
+                a[j] = ld_state(src + idx);
             }
         }
     }

@@ -32,11 +32,12 @@ def _dtype_code(dtype) -> int:
 
 
 class PlanHandle:
-    __slots__ = ("plan_id", "n_qubits", "n_params", "n_ops", "n_sweeps", "n_passes", "dtype", "__weakref__")
+    __slots__ = ("plan_id", "n_qubits", "n_params", "n_ops", "n_sweeps", "n_passes", "dtype", "prefix", "__weakref__")
 
     def __init__(self, plan_id, n_qubits, n_params, n_ops, n_sweeps, n_passes, dtype):
         self.plan_id, self.n_qubits, self.n_params = plan_id, n_qubits, n_params
         self.n_ops, self.n_sweeps, self.n_passes, self.dtype = n_ops, n_sweeps, n_passes, dtype
+        self.prefix = None  # PlanHandle of the parameter-free prefix this plan starts from (kept alive with it)
 
 
 class HamiltonianHandle:
@@ -78,6 +79,8 @@ class Engine:
         self._ctx = handle
         self._lock = threading.Lock()
         self._plan_cache: dict = {}
+        self._prefix_bytes = 0
+        self._prefix_budget = int(os.environ.get("QB_PREFIX_CACHE_MB", 16384)) << 20  # device memory for cached prefix states
         self._finalizer = weakref.finalize(self, Engine._destroy, self._lib, handle)
         if workspace_limit:
             _native.check(self._lib.qb_context_set_workspace_limit(self._ctx, int(workspace_limit)))
@@ -102,12 +105,42 @@ class Engine:
         _native.check(self._lib.qb_context_synchronize(self._ctx))
 
     # ------------------------------------------------------------------ compilation
-    def compile(self, gates: GateList, dtype=None, from_zero_state: bool = True) -> PlanHandle:
+    def compile_with_prefix_reuse(self, gates: GateList, dtype=None, min_prefix_ops: int = 4) -> PlanHandle:
+        """Like ``compile``, but a leading run of parameter-free ops (the numerically bound layers of a partially
+        parameterised EVQE circuit: evqe/evolutionary_algorithm/individual.py:288-322) is compiled as a separate plan
+        whose resulting state is computed once and cached on the device; every evaluation then only applies the
+        remaining ops.  The returned handle owns the cached state: it is not shared through
+        the structural plan cache and is released with the handle.  Falls back to ``compile`` when there is nothing
+        to reuse or the cached states would exceed a quarter of the workspace budget."""
+        split = 0
+        for op in gates.ops:
+            if any(a.slot >= 0 for a in op.angles):
+                break
+            split += 1
+        state_bytes = (16 if (self._dtype_code if dtype is None else _dtype_code(dtype)) == _native.QB_C128 else 8) << max(gates.n_qubits, self.tile_bits)
+        if split < min_prefix_ops or split == len(gates.ops) or gates.n_params == 0:
+            return self.compile(gates, dtype)
+        with self._lock:
+            if self._prefix_bytes + state_bytes > self._prefix_budget:
+                return self.compile(gates, dtype)
+            self._prefix_bytes += state_bytes
+        prefix = self.compile(GateList(gates.n_qubits, list(gates.ops[:split]), 0, ()), dtype, from_zero_state=True)
+        suffix = self.compile(GateList(gates.n_qubits, list(gates.ops[split:]), gates.n_params, gates.param_names), dtype, from_zero_state=False, cache=False)
+        _native.check(self._lib.qb_plan_set_prefix(self._ctx, suffix.plan_id, prefix.plan_id))
+        suffix.prefix = prefix
+        weakref.finalize(suffix, self._release_prefix_bytes, state_bytes)
+        return suffix
+
+    def _release_prefix_bytes(self, nbytes):
+        with self._lock:
+            self._prefix_bytes -= nbytes
+
+    def compile(self, gates: GateList, dtype=None, from_zero_state: bool = True, cache: bool = True) -> PlanHandle:
         """``from_zero_state=False``: the plan will be applied to an existing state (no product-state prefix)."""
         code = self._dtype_code if dtype is None else _dtype_code(dtype)
         key = (code, bool(from_zero_state), gates.structure_key())
         with self._lock:
-            hit = self._plan_cache.get(key)
+            hit = self._plan_cache.get(key) if cache else None
         if hit is not None:
             return hit
         plan = schedule.plan_circuit(gates.ops, gates.n_qubits, tile_bits=self.tile_bits, reg_bits=self.reg_bits, product_prefix=from_zero_state)
@@ -122,10 +155,11 @@ class Engine:
         )
         handle = PlanHandle(plan_id.value, gates.n_qubits, gates.n_params, len(gates.ops), len(sweeps), len(passes), code)
         weakref.finalize(handle, self._release_plan, self._lib, self._ctx, plan_id.value, self._finalizer)
-        with self._lock:
-            if len(self._plan_cache) > 4096:
-                self._plan_cache.clear()
-            self._plan_cache[key] = handle
+        if cache:
+            with self._lock:
+                if len(self._plan_cache) > 4096:
+                    self._plan_cache.clear()
+                self._plan_cache[key] = handle
         return handle
 
     @staticmethod

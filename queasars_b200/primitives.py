@@ -58,7 +58,8 @@ class _CircuitCache:
             if hit is not None and hit[0]() is circuit:
                 return hit[1]
         gates = from_circuit_or_none(circuit)
-        plan = None if gates is None else self._engine.compile(gates)
+        # identity-cached circuits are the ones an optimizer loop re-submits: worth caching their constant prefix state
+        plan = None if gates is None else self._engine.compile_with_prefix_reuse(gates)
         try:
             ref = weakref.ref(circuit, lambda _r, k=key: self._by_id.pop(k, None))
         except TypeError:  # not weak-referenceable: do not cache by identity

@@ -454,3 +454,30 @@ def test_sharded_api_single_rank(engine):
     e_want = float(np.dot(np.abs(want) ** 2, oq.diagonal_table(n, list(zip(z, c)))))
     assert rel_err(sv.diagonal_expectation(z, c), e_want) < 1e-10
     assert abs(sv.norm_squared() - 1.0) < 1e-12
+
+
+def test_prefix_state_reuse_matches_full_evaluation(engine):
+    """Optimizer pattern (mutation.py:57-81): one layer parameterised, the others bound numerically.  The cached
+    prefix state must give the same expectation values as evaluating the whole circuit from |0...0>."""
+    n = 14
+    terms = random_ising(n, 9)
+    ham = engine.hamiltonian(SparsePauliOp.from_list(terms))
+    table = oq.diagonal_table(n, oq.diag_terms_from_labels(terms))
+    rng = np.random.default_rng(4)
+    for lid in (-1, 1):
+        instr, values, circ = evqe_case(n, 4, 55, {lid})
+        gates = gl.from_circuit(circ)
+        reuse = engine.compile_with_prefix_reuse(gates)
+        full = engine.compile(gates)
+        if lid == -1:
+            assert reuse.prefix is not None and reuse.n_ops < full.n_ops
+        batch = [list(rng.uniform(0, 2 * math.pi, len(values))) for _ in range(5)]
+        got = engine.expectation([reuse] * 5, batch, ham)
+        ref = engine.expectation([full] * 5, batch, ham)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+        for g, v in zip(got, batch):
+            assert rel_err(g, float(np.dot(np.abs(oq.statevector(instr, n, v)) ** 2, table))) < 1e-10
+        assert np.max(np.abs(engine.statevector(reuse, batch[0]) - oq.statevector(instr, n, batch[0]))) < 1e-13
+        idx = engine.sample([reuse], [batch[0]], 2000, np.random.default_rng(1).random((1, 2000)))[0]
+        want = oq.sample_indices(oq.statevector(instr, n, batch[0]), 2000, uniforms=np.random.default_rng(1).random(2000))
+        assert np.count_nonzero(idx != want) <= 1
