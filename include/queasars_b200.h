@@ -34,7 +34,7 @@ extern "C" {
 
 #define QB_TILE_BITS 11     /* default amplitudes per CTA tile = 2^11 (a plan may choose 12) */
 #define QB_MAX_TILE_BITS 12
-#define QB_REG_BITS 4   /* default amplitudes per thread = 2^4 (a plan may choose 3: 512 threads x 8 amplitudes) */
+#define QB_REG_BITS 4   /* default amplitudes per thread = 2^4 (a plan may choose 5) */
 #define QB_LOW_BITS 4   /* lowest qubits always inside the tile (256 B contiguous runs for c128) */
 
 /* operand-position kinds inside a pass (see queasars_b200/schedule.py) */
@@ -54,7 +54,7 @@ typedef struct qb_sweep {
 } qb_sweep;
 
 typedef struct qb_pass {
-    int32_t reg_bits[4]; /* tile-local bit positions held in registers (first reg_bits entries used) */
+    int32_t reg_bits[8]; /* tile-local bit positions held in registers (first reg_bits entries used, at most 5) */
     int32_t op_begin, op_end;
     uint8_t thread_bits[12]; /* tile-local bit carried by thread-index bit i (the tile_bits - reg_bits others) */
 } qb_pass;
@@ -65,9 +65,9 @@ typedef struct qb_pass_op {
     uint8_t tgt_kind, tgt_pos;
     uint8_t ctrl_kind, ctrl_pos;
     /* pre-decoded dispatch (derived from the fields above; checked by qb_plan_create):
-     *   variant     dense: 5 * target_reg_bit + (control_reg_bit + 1)           (0..19)
-     *               diag : 20 = target outside registers, 21 + b = target register bit b, both without a
-     *                      register control; 25 = generic (register-controlled) diagonal
+     *   variant     dense: 6 * target_reg_bit + (control_reg_bit + 1)           (0..29)
+     *               diag : 32 = target outside registers, 33 + b = target register bit b, both without a
+     *                      register control; 40 = generic (register-controlled) diagonal
      *   ctrl_qubit  global qubit index of a QB_K_THREAD / QB_K_EXT control, 0xFF otherwise
      *   tgt_qubit   global qubit index of a QB_K_THREAD / QB_K_EXT diagonal target, 0xFF otherwise */
     uint8_t variant, ctrl_qubit, tgt_qubit;

@@ -364,6 +364,8 @@ int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     }
     QB_DISPATCH(4, 11)
     QB_DISPATCH(4, 12)
+    QB_DISPATCH(5, 11)
+    QB_DISPATCH(5, 12)
 #undef QB_DISPATCH
     return fail(QB_ERR_INVALID, "unsupported tile / register bit combination");
 }
@@ -533,6 +535,8 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_, uint64_t>, qb::sweep_smem_bytes<float, K_>()));
     QB_CONFIGURE(4, 11)
     QB_CONFIGURE(4, 12)
+    QB_CONFIGURE(5, 11)
+    QB_CONFIGURE(5, 12)
 #undef QB_CONFIGURE
     *out = ctx.release();
     return QB_OK;
@@ -579,7 +583,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     if (n_qubits < 1 || n_qubits > 40) return fail(QB_ERR_INVALID, "n_qubits out of range");
     if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
     if (n_sweeps < 1 || n_passes < 1) return fail(QB_ERR_INVALID, "a plan needs at least one sweep with one pass");
-    if (reg_bits != 4) return fail(QB_ERR_INVALID, "reg_bits must be 4 (3 is supported by the kernel template but not compiled in)");
+    if (reg_bits != 4 && reg_bits != 5) return fail(QB_ERR_INVALID, "reg_bits must be 4 or 5");
     const int thread_bits = tile_bits - reg_bits;
     if (tile_bits != 11 && tile_bits != 12) return fail(QB_ERR_INVALID, "tile_bits must be 11 or 12");
     const int n_eff = std::max(n_qubits, tile_bits);
@@ -631,10 +635,10 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
                 auto gq = [&](int kind, int pos) { return kind == QB_K_THREAD ? sw.tile_qubits[pos] : (kind == QB_K_EXT ? pos : 0xFF); };
                 const int cb = po.ctrl_kind == QB_K_REG ? int(po.ctrl_pos) : -1;
                 int variant, tq = 0xFF;
-                if (po.kind == QB_OP_DENSE) variant = 5 * po.tgt_pos + cb + 1;
-                else if (cb >= 0) variant = 25, tq = gq(po.tgt_kind, po.tgt_pos);
-                else if (po.tgt_kind == QB_K_REG) variant = 21 + po.tgt_pos;
-                else variant = 20, tq = gq(po.tgt_kind, po.tgt_pos);
+                if (po.kind == QB_OP_DENSE) variant = 6 * po.tgt_pos + cb + 1;
+                else if (cb >= 0) variant = 40, tq = gq(po.tgt_kind, po.tgt_pos);
+                else if (po.tgt_kind == QB_K_REG) variant = 33 + po.tgt_pos;
+                else variant = 32, tq = gq(po.tgt_kind, po.tgt_pos);
                 if (po.kind == QB_OP_DENSE && cb == int(po.tgt_pos)) return fail(QB_ERR_INVALID, "control equals target");
                 if (po.variant != variant || po.ctrl_qubit != gq(po.ctrl_kind, po.ctrl_pos) || po.tgt_qubit != tq)
                     return fail(QB_ERR_INVALID, "pre-decoded dispatch fields are inconsistent");

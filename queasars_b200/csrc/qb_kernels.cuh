@@ -22,7 +22,7 @@
 
 namespace qb {
 
-constexpr int kMaxRegBits = 4;
+constexpr int kMaxRegBits = 5;
 constexpr int kMaxSweepOps = 96;
 constexpr int kMaxSweepPasses = 16;
 
@@ -145,19 +145,6 @@ __device__ __forceinline__ void apply_dense_v(typename Cx<T>::type (&a)[1 << R],
     if constexpr (B < R && CB < R && B != CB) apply_dense<T, R, B, CB>(a, m);
 }
 
-template <typename T, int R, int B>
-__device__ __forceinline__ void apply_dense_ctrl(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m, int cb) {
-    if constexpr (B < R) {
-        switch (cb) {
-            case 0: if constexpr (B != 0 && R > 0) apply_dense<T, R, B, 0>(a, m); break;
-            case 1: if constexpr (B != 1 && R > 1) apply_dense<T, R, B, 1>(a, m); break;
-            case 2: if constexpr (B != 2 && R > 2) apply_dense<T, R, B, 2>(a, m); break;
-            case 3: if constexpr (B != 3 && R > 3) apply_dense<T, R, B, 3>(a, m); break;
-            default: apply_dense<T, R, B, -1>(a, m); break;
-        }
-    }
-}
-
 template <typename T>
 __device__ __forceinline__ typename Cx<T>::type cmul(typename Cx<T>::type a, typename Cx<T>::type b) {
     typename Cx<T>::type r;
@@ -181,7 +168,7 @@ __device__ __forceinline__ U reg_offset(int j, const U (&off)[R]) {
 // sweep kernel: grid = (tiles, active batch entries), block = 256 threads, dynamic smem = sweep_smem_bytes<T>()
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int R, int K, typename Idx>
-__global__ void __launch_bounds__(1 << (K - R), (K <= 11 ? 4 : 2))
+__global__ void __launch_bounds__(1 << (K - R), (R == 5 ? (K <= 11 ? 4 : 2) : (K <= 11 ? 4 : 2)))
 // (K - R <= 8: the scatter tables cover at most 8 thread-index bits)
 sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation) {
     using C = typename Cx<T>::type;
@@ -366,24 +353,26 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             const C* m = s_mat + o * 4;
             switch (word & 0xffu) {
 #define QB_DENSE_CASES(B)                                                    \
-    case 5 * B + 0: apply_dense_v<T, R, B, -1>(a, m); break;                  \
-    case 5 * B + 1: apply_dense_v<T, R, B, 0>(a, m); break;                   \
-    case 5 * B + 2: apply_dense_v<T, R, B, 1>(a, m); break;                   \
-    case 5 * B + 3: apply_dense_v<T, R, B, 2>(a, m); break;                   \
-    case 5 * B + 4: apply_dense_v<T, R, B, 3>(a, m); break;
+    case 6 * B + 0: apply_dense_v<T, R, B, -1>(a, m); break;                  \
+    case 6 * B + 1: apply_dense_v<T, R, B, 0>(a, m); break;                   \
+    case 6 * B + 2: apply_dense_v<T, R, B, 1>(a, m); break;                   \
+    case 6 * B + 3: apply_dense_v<T, R, B, 2>(a, m); break;                   \
+    case 6 * B + 4: apply_dense_v<T, R, B, 3>(a, m); break;                   \
+    case 6 * B + 5: apply_dense_v<T, R, B, 4>(a, m); break;
                 QB_DENSE_CASES(0)
                 QB_DENSE_CASES(1)
                 QB_DENSE_CASES(2)
                 QB_DENSE_CASES(3)
+                QB_DENSE_CASES(4)
 #undef QB_DENSE_CASES
-                case 20: {  // diagonal, target bit outside the registers: one factor for all amplitudes
+                case 32: {  // diagonal, target bit outside the registers: one factor for all amplitudes
                     const C d = ((W >> ((word >> 16) & 0xffu)) & 1ull) ? m[3] : m[0];
 #pragma unroll
                     for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], d);
                     break;
                 }
-                case 21: case 22: case 23: case 24: {  // diagonal on a register bit
-                    const uint32_t tb = 1u << ((word & 0xffu) - 21u);
+                case 33: case 34: case 35: case 36: case 37: {  // diagonal on a register bit
+                    const uint32_t tb = 1u << ((word & 0xffu) - 33u);
                     const C d0 = m[0], d1 = m[3];
 #pragma unroll
                     for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);

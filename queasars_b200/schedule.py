@@ -275,7 +275,7 @@ def plan_circuit(
 # flat encoding handed to the C-ABI (layout documented in include/queasars_b200.h)
 # -------------------------------------------------------------------------------------------------
 SWEEP_DTYPE = np.dtype([("tile_qubits", np.int32, (16,)), ("pass_begin", np.int32), ("pass_end", np.int32), ("op_begin", np.int32), ("op_end", np.int32)], align=True)
-PASS_DTYPE = np.dtype([("reg_bits", np.int32, (4,)), ("op_begin", np.int32), ("op_end", np.int32), ("thread_bits", np.uint8, (12,))], align=True)
+PASS_DTYPE = np.dtype([("reg_bits", np.int32, (8,)), ("op_begin", np.int32), ("op_end", np.int32), ("thread_bits", np.uint8, (12,))], align=True)
 PASSOP_DTYPE = np.dtype(
     [("op_index", np.int32), ("kind", np.uint8), ("tgt_kind", np.uint8), ("tgt_pos", np.uint8), ("ctrl_kind", np.uint8), ("ctrl_pos", np.uint8), ("variant", np.uint8), ("ctrl_qubit", np.uint8), ("tgt_qubit", np.uint8)],
     align=True,
@@ -295,17 +295,17 @@ def _predecode(po: PassOp, tile_qubits: Sequence[int]) -> tuple[int, int, int]:
     cb = po.ctrl_pos if po.ctrl_kind == K_REG else -1
     cq = global_qubit(po.ctrl_kind, po.ctrl_pos)
     if po.kind == DENSE:
-        return 5 * po.tgt_pos + (cb + 1), cq, 0xFF
+        return 6 * po.tgt_pos + (cb + 1), cq, 0xFF
     if cb >= 0:
-        return 25, cq, global_qubit(po.tgt_kind, po.tgt_pos)
+        return 40, cq, global_qubit(po.tgt_kind, po.tgt_pos)
     if po.tgt_kind == K_REG:
-        return 21 + po.tgt_pos, cq, 0xFF
-    return 20, cq, global_qubit(po.tgt_kind, po.tgt_pos)
+        return 33 + po.tgt_pos, cq, 0xFF
+    return 32, cq, global_qubit(po.tgt_kind, po.tgt_pos)
 
 
 def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
     """-> (sweeps, passes, pass_ops, op_angles, init_ops) arrays."""
-    assert plan.tile_bits <= 16 and plan.reg_bits in (3, 4)
+    assert plan.tile_bits <= 16 and plan.reg_bits in (4, 5)
     sweeps = np.zeros(len(plan.sweeps), dtype=SWEEP_DTYPE)
     passes = np.zeros(plan.n_passes, dtype=PASS_DTYPE)
     pass_ops = np.zeros(max(1, sum(s.n_ops for s in plan.sweeps)), dtype=PASSOP_DTYPE)

@@ -21,7 +21,7 @@ def op_matrix(angle_rec, params):
     )
 
 
-def run_program(encoded, n_eff, tile_bits, params, state=None):
+def run_program(encoded, n_eff, tile_bits, params, state=None, reg_bits=4):
     sweeps, passes, pass_ops, angles, init_ops = encoded
     size = 1 << n_eff
     if state is None:
@@ -48,8 +48,8 @@ def run_program(encoded, n_eff, tile_bits, params, state=None):
             idx = base | goff
             tile = state[idx]
             for ps in passes[sw["pass_begin"] : sw["pass_end"]]:
-                reg = [int(b) for b in ps["reg_bits"]]
-                assert len(set(reg)) == 4 and all(0 <= b < tile_bits for b in reg)
+                reg = [int(b) for b in ps["reg_bits"][:reg_bits]]
+                assert len(set(reg)) == reg_bits and all(0 <= b < tile_bits for b in reg)
                 for po in pass_ops[ps["op_begin"] : ps["op_end"]]:
                     m = op_matrix(angles[po["op_index"]], params)
 

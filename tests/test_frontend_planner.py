@@ -39,7 +39,7 @@ def build_circuit(instructions, n):
 def emulate(gates: gl.GateList, values, k=sc.TILE_BITS, r=4, low=4):
     plan = sc.plan_circuit(gates.ops, gates.n_qubits, k, r, low)
     enc = sc.encode_plan(plan, gates.ops)
-    state = run_program(enc, plan.n_eff, k, list(values))
+    state = run_program(enc, plan.n_eff, k, list(values), reg_bits=r)
     assert np.allclose(state[1 << gates.n_qubits :], 0)
     return state[: 1 << gates.n_qubits], plan
 
@@ -57,7 +57,7 @@ def test_evqe_circuits_through_planner(n, layers, seed):
     np.testing.assert_allclose(got, want, atol=1e-13)
 
 
-@pytest.mark.parametrize("k,r,low", [(6, 4, 2), (7, 4, 3), (8, 4, 4)])
+@pytest.mark.parametrize("k,r,low", [(6, 4, 2), (7, 4, 3), (8, 4, 4), (9, 5, 3)])
 @pytest.mark.parametrize("n,layers,seed", [(8, 3, 10), (10, 4, 11), (11, 2, 12)])
 def test_small_tiles_exercise_multi_tile_paths(k, r, low, n, layers, seed):
     genome, values = og.random_individual(n, layers, True, seed)
