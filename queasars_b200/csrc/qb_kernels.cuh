@@ -168,7 +168,7 @@ __device__ __forceinline__ U reg_offset(int j, const U (&off)[R]) {
 // sweep kernel: grid = (tiles, active batch entries), block = 256 threads, dynamic smem = sweep_smem_bytes<T>()
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int R, int K, typename Idx>
-__global__ void __launch_bounds__(1 << (K - R), (R == 5 ? (K <= 11 ? 4 : 2) : (K <= 11 ? 4 : 2)))
+__global__ void __launch_bounds__(1 << (K - R), (K <= 11 ? 4 : 2))
 // (K - R <= 8: the scatter tables cover at most 8 thread-index bits)
 sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation) {
     using C = typename Cx<T>::type;
