@@ -43,6 +43,8 @@ extern "C" {
 #define QB_K_THREAD 2 /* pos = tile-local bit held in the thread index   */
 #define QB_K_EXT 3    /* pos = global qubit outside the tile             */
 
+#define QB_PASS_WARP_LOCAL 1
+
 #define QB_OP_DENSE 0 /* e^{i gamma} U(theta,phi,lam) on target [, control]            */
 #define QB_OP_DIAG 1  /* diag(e^{i gamma}, e^{i(gamma+lam)}) on target [, control]     */
 
@@ -54,7 +56,9 @@ typedef struct qb_sweep {
 } qb_sweep;
 
 typedef struct qb_pass {
-    int32_t reg_bits[8]; /* tile-local bit positions held in registers (first reg_bits entries used, at most 5) */
+    int32_t reg_bits[7]; /* tile-local bit positions held in registers (first reg_bits entries used, at most 5) */
+    int32_t flags;       /* bit 0 (QB_PASS_WARP_LOCAL): the next pass keeps the same tile bits on the warp-index bits, so the
+                            shared-memory exchange after this pass needs __syncwarp only */
     int32_t op_begin, op_end;
     uint8_t thread_bits[12]; /* tile-local bit carried by thread-index bit i (the tile_bits - reg_bits others) */
 } qb_pass;

@@ -618,6 +618,11 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
                 used |= 1u << b;
             }
             if (p > sw.pass_begin && ps.op_begin != passes[p - 1].op_end) return fail(QB_ERR_INVALID, "pass op ranges must be contiguous");
+            if (ps.flags & QB_PASS_WARP_LOCAL) {  // claim must hold: same tile bits on the warp-index bits of the next pass
+                if (p + 1 >= sw.pass_end) return fail(QB_ERR_INVALID, "warp-local flag on the last pass of a sweep");
+                for (int i = 5; i < thread_bits; ++i)
+                    if (ps.thread_bits[i] != passes[p + 1].thread_bits[i]) return fail(QB_ERR_INVALID, "warp-local exchange with different warp bits");
+            }
             for (int o = ps.op_begin; o < ps.op_end; ++o) {
                 const qb_pass_op& po = pass_ops[o];
                 if (po.op_index < 0 || po.op_index >= n_ops) return fail(QB_ERR_INVALID, "op index out of range");

@@ -412,13 +412,16 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                 if (tid == 0) en.partials[blockIdx.x] = total;
             }
         } else {
-            if (!first) __syncthreads();  // everyone finished reading the previous layout
+            // every thread writes back exactly the shared-memory slots it loaded in this pass: no hazard before the store
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
                 const uint32_t si = s_thr ^ reg_offset<kRegBits>(j, so);
                 tile[si] = a[j];
             }
-            __syncthreads();
+            // the next pass re-reads the tile in its own layout: CTA barrier, unless both passes keep the same tile bits on
+            // the warp-index bits -- then every warp only reads what it wrote itself
+            if (ps.flags & QB_PASS_WARP_LOCAL) __syncwarp();
+            else __syncthreads();
         }
     }
 }

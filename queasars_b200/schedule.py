@@ -33,6 +33,8 @@ LOW_BITS = 4
 MAX_SWEEP_OPS = 96  # csrc/qb_kernels.cuh kMaxSweepOps
 MAX_SWEEP_PASSES = 16  # kMaxSweepPasses
 
+PASS_FLAG_WARP_LOCAL = 1  # qb_pass.flags bit 0
+
 # position kinds in the encoded program
 K_NONE, K_REG, K_THREAD, K_EXT = 0, 1, 2, 3
 
@@ -52,6 +54,7 @@ class PassPlan:
     reg_bits: list[int] = field(default_factory=list)  # tile-local positions held in registers
     ops: list[PassOp] = field(default_factory=list)
     thread_bits: list[int] = field(default_factory=list)  # tile-local position of thread-index bit i
+    warp_local_exchange: bool = False  # the exchange AFTER this pass stays inside each warp (no CTA barrier needed)
 
 
 @dataclass
@@ -116,22 +119,31 @@ def _select_sweep(ops: Sequence[KernelOp], remaining: list[int], n_eff: int, k: 
     return sorted(tile), chosen, rest
 
 
-def _thread_bit_order(reg: list[int], k: int, low: int) -> list[int]:
-    """Which tile-local bit each thread-index bit carries.  Passes that touch global memory (no low bit in
-    registers) keep ascending order so lanes 0..2^low-1 walk contiguous amplitudes.  Pure shared-memory
-    passes are free to choose: the shared-memory layout XOR-folds the index in groups of three bits
-    (qb_kernels.cuh: swizzle), so lane bits 0-2 are picked from three different (position mod 3) classes
-    whenever possible, which makes the 128-bit accesses of a quarter warp conflict-free."""
+def _thread_bit_order(reg: list[int], k: int, low: int, warp_pos: Sequence[int] = ()) -> list[int]:
+    """Which tile-local bit each thread-index bit carries: first the 5 lane bits, then the warp-index bits.
+
+    * Passes that touch global memory (no low bit in registers) keep the ``low`` lowest tile bits on lanes 0.. so lanes
+      walk contiguous amplitudes.  Pure shared-memory passes pick lane bits 0-2 from three different
+      (position mod 3) classes when possible: the shared-memory layout XOR-folds the index in groups of three bits
+      (qb_kernels.cuh: swz), which keeps the 128-bit accesses of a quarter warp conflict-free.
+    * ``warp_pos``: tile positions the sweep wants on the warp-index bits (the highest thread-index bits).  When two
+      consecutive passes carry the same positions there, every warp reads back exactly the amplitudes it wrote and the
+      exchange between them needs ``__syncwarp`` only."""
     free = [b for b in range(k) if b not in reg]
+    n_warp = max(0, len(free) - 5)
+    warp = [b for b in warp_pos if b in free][:n_warp]
+    rest = [b for b in free if b not in warp]
+    while len(warp) < n_warp:  # not enough preferred positions available in this pass: take the highest free ones
+        warp.insert(0, rest.pop())
     if not any(b < low for b in reg):
-        return free
+        return rest + warp
     picked: list[int] = []
     for cls in range(3):
-        for b in free:
+        for b in rest:
             if b % 3 == cls and b not in picked:
                 picked.append(b)
                 break
-    return picked + [b for b in free if b not in picked]
+    return picked + [b for b in rest if b not in picked] + warp
 
 
 def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[int], r: int, low: int) -> list[PassPlan]:
@@ -183,16 +195,44 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
     if len(regs) > 1 and not members[0] and not any(b < low for b in regs[1]):
         regs.pop(0), allow_low.pop(0), members.pop(0)
 
-    passes: list[PassPlan] = []
-    for reg, mem in zip(regs, members):
+    # pad every register set to r positions (positions nobody targets, highest first)
+    padded: list[list[int]] = []
+    for idx, reg in enumerate(regs):
         reg = list(reg)
-        cand = k - 1
-        while len(reg) < min(r, k):
-            if cand not in reg:
+        for cand in range(k - 1, -1, -1):
+            if len(reg) >= min(r, k):
+                break
+            if cand not in reg and (cand >= low or allow_low[idx]):
                 reg.append(cand)
-            cand -= 1
-        reg.sort()
-        plan = PassPlan(reg_bits=reg, thread_bits=_thread_bit_order(reg, k, low))
+        padded.append(sorted(reg))
+    # Tile positions carried by the warp-index bits, pass by pass: keep the previous pass's choice whenever those
+    # positions are still outside the register set (then the exchange between the two passes stays inside each warp),
+    # otherwise prefer positions that stay free for the longest run of following passes.
+    n_warp = max(0, k - r - 5)
+
+    def warp_candidates(idx: int) -> list[int]:
+        direct = not any(b < low for b in padded[idx])  # lanes 0..low-1 must carry the low tile bits
+        return [b for b in range(k) if b not in padded[idx] and not (direct and b < low)]
+
+    warp_choice: list[list[int]] = []
+    for idx in range(len(padded)):
+        cand = warp_candidates(idx)
+        keep = [b for b in (warp_choice[-1] if warp_choice else []) if b in cand]
+
+        def free_run(b: int) -> int:
+            run = 0
+            for nxt in range(idx + 1, len(padded)):
+                if b not in warp_candidates(nxt):
+                    break
+                run += 1
+            return run
+
+        others = sorted((b for b in cand if b not in keep), key=lambda b: (-free_run(b), -b))
+        warp_choice.append(sorted((keep + others)[:n_warp]))
+
+    passes: list[PassPlan] = []
+    for reg, mem, warp_pos in zip(padded, members, warp_choice):
+        plan = PassPlan(reg_bits=reg, thread_bits=_thread_bit_order(reg, k, low, warp_pos))
         for i in mem:
             op = ops[i]
 
@@ -208,6 +248,8 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
             ck, cpos = (K_NONE, 0) if op.control < 0 else locate(op.control)
             plan.ops.append(PassOp(i, op.kind, tk, tpos, ck, cpos))
         passes.append(plan)
+    for a, b in zip(passes, passes[1:]):
+        a.warp_local_exchange = n_warp > 0 and a.thread_bits[5:] == b.thread_bits[5:]
     return passes
 
 
@@ -275,7 +317,7 @@ def plan_circuit(
 # flat encoding handed to the C-ABI (layout documented in include/queasars_b200.h)
 # -------------------------------------------------------------------------------------------------
 SWEEP_DTYPE = np.dtype([("tile_qubits", np.int32, (16,)), ("pass_begin", np.int32), ("pass_end", np.int32), ("op_begin", np.int32), ("op_end", np.int32)], align=True)
-PASS_DTYPE = np.dtype([("reg_bits", np.int32, (8,)), ("op_begin", np.int32), ("op_end", np.int32), ("thread_bits", np.uint8, (12,))], align=True)
+PASS_DTYPE = np.dtype([("reg_bits", np.int32, (7,)), ("flags", np.int32), ("op_begin", np.int32), ("op_end", np.int32), ("thread_bits", np.uint8, (12,))], align=True)
 PASSOP_DTYPE = np.dtype(
     [("op_index", np.int32), ("kind", np.uint8), ("tgt_kind", np.uint8), ("tgt_pos", np.uint8), ("ctrl_kind", np.uint8), ("ctrl_pos", np.uint8), ("variant", np.uint8), ("ctrl_qubit", np.uint8), ("tgt_qubit", np.uint8)],
     align=True,
@@ -317,6 +359,7 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
         for ps in sw.passes:
             passes[pi]["reg_bits"][: len(ps.reg_bits)] = ps.reg_bits
             passes[pi]["thread_bits"][: len(ps.thread_bits)] = ps.thread_bits
+            passes[pi]["flags"] = PASS_FLAG_WARP_LOCAL if ps.warp_local_exchange else 0
             passes[pi]["op_begin"] = oi
             for po in ps.ops:
                 rec = pass_ops[oi]
