@@ -261,7 +261,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
     b.n_state_sweeps = 0;
     for (int i = 0; i < batch; ++i) {
         b.param_begin[i + 1] = b.param_begin[i] + plans[i]->n_params;
-        op_begin[i + 1] = op_begin[i] + plans[i]->n_ops + plans[i]->n_pass_ops;
+        op_begin[i + 1] = op_begin[i] + plans[i]->n_ops + plans[i]->n_pass_ops + (plans[i]->n_eff + 1) / 2;  // + 4 doubles per qubit
         for (int s = 0; s < plans[i]->n_sweeps; ++s) b.active[s]++;
         b.n_state_sweeps += plans[i]->n_sweeps;
     }
@@ -304,7 +304,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         en.n_sweeps = pl->n_sweeps;
         en.n_ops = pl->n_ops;
         en.n_pass_ops = pl->n_pass_ops;
-        en.pad = 0;
+        en.n_init = pl->n_eff;
         en.n_params = pl->n_params;
         en.init_zero = pl->prefix_id ? 0 : init_zero;
         en.index_offset = index_offset;

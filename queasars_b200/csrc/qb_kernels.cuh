@@ -39,13 +39,13 @@ struct BatchEntry {
     const qb_op_angles* angles;
     const int32_t* init_ops;   // device, n_eff entries (product-state start) or nullptr
     const double* params;      // device, n_params
-    double* matrices;          // device, (n_ops + n_pass_ops) * 8: bound 2x2 matrices by op index, then again in pass-op order
+    double* matrices;          // device: 8 doubles per op (by op index), 8 per pass-op (pass order), 4 per qubit (initial state)
     void* state;               // device, 2^n_eff amplitudes
     const void* src_state;     // optional: the first sweep reads this (cached prefix state) instead of `state`
     const double* diag_table;  // device, 2^n_eff doubles, or nullptr
     double* partials;          // device, one double per tile (fused expectation epilogue)
     int32_t n_sweeps, n_ops, n_params, init_zero;
-    int32_t n_pass_ops, pad;
+    int32_t n_pass_ops, n_init;  // n_init = number of init_ops entries (= padded qubit count)
     uint64_t index_offset;
 };
 
@@ -249,44 +249,44 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
         setup_pass(ps);
         if (sweep_idx == 0 && en.init_zero && en.init_ops != nullptr) {
             // product-state start: amplitude(k) = prod_q v_q[bit_q(k)], v_q = first column of qubit q's first
-            // gate (or |0>).  The 2 * n_eff single-qubit amplitudes are staged in shared memory (reusing the tile
-            // buffer, which nothing has touched yet); P collects the factors of all index bits shared by this
+            // gate (or |0>), written per qubit by bind_kernel.  P collects the factors of all index bits shared by this
             // thread's amplitudes, the register bits are expanded by doubling.
-            C* s_init = tile;  // [q][0 | 1]
-            for (int i = tid; i < 2 * n_eff; i += kThreads) {
-                const int op = en.init_ops[i >> 1];
-                C v;
-                v.x = (i & 1) ? T(0) : T(1), v.y = T(0);
-                if (op >= 0) {
-                    const double* m = en.matrices + size_t(op) * 8 + ((i & 1) ? 4 : 0);
-                    v.x = T(m[0]), v.y = T(m[1]);
-                }
-                s_init[i] = v;
-            }
-            __syncthreads();
+            const double2* __restrict__ init_vec = reinterpret_cast<const double2*>(en.matrices + (size_t(en.n_ops) + size_t(en.n_pass_ops)) * 8);
             const uint64_t Wi = gbase | g_thr;
             uint64_t reg_qubits = 0;
 #pragma unroll
             for (int i = 0; i < kRegBits; ++i) reg_qubits |= go[i];
-            C P;
-            P.x = T(1), P.y = T(0);
-            for (int q = 0; q < n_eff; ++q) {
-                if ((reg_qubits >> q) & 1ull) continue;
-                P = cmul<T>(P, s_init[2 * q + int((Wi >> q) & 1ull)]);
+            // the addresses depend only on this thread's index bits: the loads are independent and pipeline freely
+            C Pp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Pp[i].x = T(1), Pp[i].y = T(0);
+            for (int q0 = 0; q0 < n_eff; q0 += 4) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = q0 + i;
+                    if (q < n_eff && !((reg_qubits >> q) & 1ull)) {
+                        const double2 v = __ldg(init_vec + 2 * q + int((Wi >> q) & 1ull));
+                        C vv;
+                        vv.x = T(v.x), vv.y = T(v.y);
+                        Pp[i] = cmul<T>(Pp[i], vv);
+                    }
+                }
             }
+            C P = cmul<T>(cmul<T>(Pp[0], Pp[1]), cmul<T>(Pp[2], Pp[3]));
             if ((en.index_offset >> n_eff) != 0) P.x = T(0), P.y = T(0);  // rank bits above the local register start in |0>
             a[0] = P;
 #pragma unroll
             for (int i = 0; i < kRegBits; ++i) {
                 const int q = s_sweep.tile_qubits[ps.reg_bits[i]];
-                const C v0 = s_init[2 * q], v1 = s_init[2 * q + 1];
+                const double2 w0 = __ldg(init_vec + 2 * q), w1 = __ldg(init_vec + 2 * q + 1);
+                C v0, v1;
+                v0.x = T(w0.x), v0.y = T(w0.y), v1.x = T(w1.x), v1.y = T(w1.y);
 #pragma unroll
                 for (int j = 0; j < (1 << i); ++j) {
                     a[j | (1 << i)] = cmul<T>(a[j], v1);
                     a[j] = cmul<T>(a[j], v0);
                 }
             }
-            __syncthreads();  // s_init aliases the tile buffer: everyone is done reading before a pass may overwrite it
         } else if (sweep_idx == 0 && en.init_zero) {
 #pragma unroll
             for (int j = 0; j < kNReg; ++j) {
@@ -461,6 +461,21 @@ __global__ void bind_kernel(const BatchEntry* __restrict__ entries) {
     for (int o = threadIdx.x; o < en.n_ops; o += blockDim.x) bind_matrix(en.angles[o], en.params, en.matrices + size_t(o) * 8);
     for (int i = threadIdx.x; i < en.n_pass_ops; i += blockDim.x)
         bind_matrix(en.angles[en.pass_ops[i].op_index], en.params, en.matrices + (size_t(en.n_ops) + size_t(i)) * 8);
+    // product-state start: per qubit the two amplitudes (re, im, re, im) of its initial single-qubit state
+    if (en.init_ops != nullptr) {
+        double* init_vec = en.matrices + (size_t(en.n_ops) + size_t(en.n_pass_ops)) * 8;
+        for (int q = threadIdx.x; q < en.n_init; q += blockDim.x) {
+            double v[4] = {1.0, 0.0, 0.0, 0.0};
+            const int op = en.init_ops[q];
+            if (op >= 0) {
+                double m[8];
+                bind_matrix(en.angles[op], en.params, m);
+                v[0] = m[0], v[1] = m[1], v[2] = m[4], v[3] = m[5];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) init_vec[4 * q + i] = v[i];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
