@@ -34,7 +34,7 @@ extern "C" {
 
 #define QB_TILE_BITS 11     /* default amplitudes per CTA tile = 2^11 (a plan may choose 12) */
 #define QB_MAX_TILE_BITS 12
-#define QB_REG_BITS 4   /* default amplitudes per thread = 2^4 (a plan may choose 5) */
+#define QB_REG_BITS 4   /* amplitudes per thread = 2^4 */
 #define QB_LOW_BITS 4   /* lowest qubits always inside the tile (256 B contiguous runs for c128) */
 
 /* operand-position kinds inside a pass (see queasars_b200/schedule.py) */
@@ -56,7 +56,7 @@ typedef struct qb_sweep {
 } qb_sweep;
 
 typedef struct qb_pass {
-    int32_t reg_bits[7]; /* tile-local bit positions held in registers (first reg_bits entries used, at most 5) */
+    int32_t reg_bits[7]; /* tile-local bit positions held in registers (first QB_REG_BITS entries used) */
     int32_t flags;       /* bit 0 (QB_PASS_WARP_LOCAL): the next pass keeps the same tile bits on the warp-index bits, so the
                             shared-memory exchange after this pass needs __syncwarp only */
     int32_t op_begin, op_end;
@@ -68,7 +68,8 @@ typedef struct qb_pass_op {
     uint8_t kind;     /* QB_OP_*  */
     uint8_t tgt_kind, tgt_pos;
     uint8_t ctrl_kind, ctrl_pos;
-    /* pre-decoded dispatch (derived from the fields above; checked by qb_plan_create):
+    /* pre-decoded operands (derived from the fields above; checked by qb_plan_create; the kernel builds its own dispatch word
+     * from the descriptive fields when it stages a sweep, these stay for host-side tools):
      *   variant     dense: 6 * target_reg_bit + (control_reg_bit + 1)           (0..29)
      *               diag : 32 = target outside registers, 33 + b = target register bit b, both without a
      *                      register control; 40 = generic (register-controlled) diagonal

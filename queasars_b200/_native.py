@@ -83,12 +83,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("QB_NATIVE_LIB", LIB_PATH)  # development aid: A/B a differently built library
+    if not os.path.exists(path):
         raise NativeLibraryError(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  queasars_b200 has no CPU fallback."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     _declare(lib)
     sizes = (c_int32 * 4)()
     lib.qb_record_sizes(sizes)

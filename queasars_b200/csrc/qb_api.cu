@@ -130,6 +130,7 @@ struct DeviceBatch {
     const Ham* ham = nullptr;
     bool fuse_expect = false;
     size_t n_tiles = 0, partial_stride = 0;
+    int tiles_log2 = 0;  // every sweep CTA walks 2^tiles_log2 consecutive tiles (and writes ONE fused-expectation partial)
     int64_t n_state_sweeps = 0, launches_per_run = 0;
     DevBuf entries, params, matrices, partials, out, states;
     bool owns_states = true;
@@ -150,6 +151,7 @@ struct qb_context {
     uint64_t default_workspace = uint64_t(8) << 30;  // 80 % of the memory free at creation (cudaMemGetInfo is slow: ask once)
     int64_t launches = 0;
     int64_t next_id = 1;
+    int tiles_log2 = 2;  // tiles per sweep CTA (log2); QB_TILES_LOG2 overrides (measured best: 4 tiles)
     std::mutex mu;
     std::map<int64_t, std::unique_ptr<Plan>> plans;
     std::map<int64_t, std::unique_ptr<Ham>> hams;
@@ -249,6 +251,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         return fail(QB_ERR_INVALID, "Hamiltonian acts on " + std::to_string(ham->n_qubits) + " qubits, circuits on " + std::to_string(b.n_qubits));
     b.fuse_expect = ham && ham->table.p && ham->table_n_eff == b.n_eff && index_offset == 0;  // diagonal part in the last sweep
     b.n_tiles = size_t(1) << (b.n_eff - b.tile_bits);
+    b.tiles_log2 = std::min(ctx->tiles_log2, b.n_eff - b.tile_bits);
     b.partial_stride = std::max<size_t>(size_t(1) << (b.n_eff - std::min(b.n_eff, qb::kExpTileBits)), std::max<size_t>(b.n_tiles, 1024));
 
     b.order.resize(batch);
@@ -338,12 +341,14 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
     return QB_OK;
 }
 
-template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
-    const size_t smem = qb::sweep_smem_bytes<T, K>();
+template <typename T, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
+    constexpr int R = QB_REG_BITS;
     for (int s = 0; s < b.max_sweeps; ++s) {
-        dim3 grid(unsigned(b.n_tiles), unsigned(b.active[s]));
+        // every CTA stages its circuit's sweep program once and walks 2^tiles_log2 consecutive tiles with it
+        dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(b.active[s]));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s], ctx->stream));
-        qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), smem, ctx->stream>>>(b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0);
+        qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), qb::sweep_smem_bytes<T, R, K>(), ctx->stream>>>(
+            b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0, b.tiles_log2);
         QB_TRY(check_launch(ctx, "sweep_kernel"));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s + 1], ctx->stream));
     }
@@ -354,20 +359,18 @@ int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     qb::bind_kernel<<<b.batch, 128, 0, ctx->stream>>>(b.entries.as<qb::BatchEntry>());
     QB_TRY(check_launch(ctx, "bind_kernel"));
     // amplitude indices fit 32 bits up to 31 local qubits: cheaper address arithmetic for the common sizes
-#define QB_DISPATCH(R_, K_)                                                                                           \
-    if (b.reg_bits == R_ && b.tile_bits == K_) {                                                                      \
-        if (b.n_eff <= 31)                                                                                            \
-            return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_, uint32_t>(ctx, b, events)                     \
-                                      : launch_sweeps_t<float, R_, K_, uint32_t>(ctx, b, events);                     \
-        return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_, uint64_t>(ctx, b, events)                         \
-                                  : launch_sweeps_t<float, R_, K_, uint64_t>(ctx, b, events);                         \
+#define QB_DISPATCH(K_)                                                                                            \
+    if (b.tile_bits == K_) {                                                                                       \
+        if (b.n_eff <= 31)                                                                                         \
+            return b.dtype == QB_C128 ? launch_sweeps_t<double, K_, uint32_t>(ctx, b, events)                      \
+                                      : launch_sweeps_t<float, K_, uint32_t>(ctx, b, events);                      \
+        return b.dtype == QB_C128 ? launch_sweeps_t<double, K_, uint64_t>(ctx, b, events)                          \
+                                  : launch_sweeps_t<float, K_, uint64_t>(ctx, b, events);                          \
     }
-    QB_DISPATCH(4, 11)
-    QB_DISPATCH(4, 12)
-    QB_DISPATCH(5, 11)
-    QB_DISPATCH(5, 12)
+    QB_DISPATCH(11)
+    QB_DISPATCH(12)
 #undef QB_DISPATCH
-    return fail(QB_ERR_INVALID, "unsupported tile / register bit combination");
+    return fail(QB_ERR_INVALID, "unsupported tile bit count");
 }
 
 // expectation of one resident state with the generic (non-fused) kernels; result accumulated into d_out[0]
@@ -418,7 +421,7 @@ template <typename T> int launch_expectation_t(qb_context* ctx, DeviceBatch& b) 
     const int blocks = int(std::min<uint64_t>(1024, std::max<uint64_t>(1, size / 256)));
     // ---- diagonal part
     if (b.fuse_expect) {
-        QB_TRY(reduce(int64_t(b.n_tiles)));
+        QB_TRY(reduce(int64_t(b.n_tiles >> b.tiles_log2)));
     } else if (ham.n_diag > 0) {
         const bool table = ham.table.p && ham.table_n_eff == b.n_eff;
         const Group* dg = ham.groups.front().get();  // the x == 0 group is stored first
@@ -528,16 +531,15 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     }
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_in_done, cudaEventDisableTiming));
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_entries_done, cudaEventDisableTiming));
-#define QB_CONFIGURE(R_, K_)                                                                                            \
-    QB_TRY(configure_kernel(qb::sweep_kernel<double, R_, K_, uint32_t>, qb::sweep_smem_bytes<double, K_>())); \
-    QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_, uint32_t>, qb::sweep_smem_bytes<float, K_>()));   \
-    QB_TRY(configure_kernel(qb::sweep_kernel<double, R_, K_, uint64_t>, qb::sweep_smem_bytes<double, K_>())); \
-    QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_, uint64_t>, qb::sweep_smem_bytes<float, K_>()));
-    QB_CONFIGURE(4, 11)
-    QB_CONFIGURE(4, 12)
-    QB_CONFIGURE(5, 11)
-    QB_CONFIGURE(5, 12)
+#define QB_CONFIGURE(K_)                                                                                                \
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, QB_REG_BITS, K_, uint32_t>, qb::sweep_smem_bytes<double, QB_REG_BITS, K_>())); \
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, QB_REG_BITS, K_, uint32_t>, qb::sweep_smem_bytes<float, QB_REG_BITS, K_>()));   \
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, QB_REG_BITS, K_, uint64_t>, qb::sweep_smem_bytes<double, QB_REG_BITS, K_>())); \
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, QB_REG_BITS, K_, uint64_t>, qb::sweep_smem_bytes<float, QB_REG_BITS, K_>()));
+    QB_CONFIGURE(11)
+    QB_CONFIGURE(12)
 #undef QB_CONFIGURE
+    if (const char* e = std::getenv("QB_TILES_LOG2")) ctx->tiles_log2 = std::max(0, std::atoi(e));
     *out = ctx.release();
     return QB_OK;
 }
@@ -583,7 +585,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     if (n_qubits < 1 || n_qubits > 40) return fail(QB_ERR_INVALID, "n_qubits out of range");
     if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
     if (n_sweeps < 1 || n_passes < 1) return fail(QB_ERR_INVALID, "a plan needs at least one sweep with one pass");
-    if (reg_bits != 4 && reg_bits != 5) return fail(QB_ERR_INVALID, "reg_bits must be 4 or 5");
+    if (reg_bits != QB_REG_BITS) return fail(QB_ERR_INVALID, "reg_bits must be 4");
     const int thread_bits = tile_bits - reg_bits;
     if (tile_bits != 11 && tile_bits != 12) return fail(QB_ERR_INVALID, "tile_bits must be 11 or 12");
     const int n_eff = std::max(n_qubits, tile_bits);

@@ -22,7 +22,6 @@
 
 namespace qb {
 
-constexpr int kMaxRegBits = 5;
 constexpr int kMaxSweepOps = 96;
 constexpr int kMaxSweepPasses = 16;
 
@@ -48,12 +47,6 @@ struct BatchEntry {
     int32_t n_pass_ops, n_init;  // n_init = number of init_ops entries (= padded qubit count)
     uint64_t index_offset;
 };
-
-template <typename T, int K>
-constexpr size_t sweep_smem_bytes() {
-    return sizeof(typename Cx<T>::type) * (size_t(1) << K) + sizeof(T) * 8 * kMaxSweepOps + sizeof(qb_pass_op) * kMaxSweepOps +
-           sizeof(qb_pass) * kMaxSweepPasses + sizeof(uint32_t) * (kMaxSweepOps + 1);
-}
 
 // XOR-fold of the tile-local index in groups of three bits: linear over GF(2), so
 // swz(a | b) == swz(a) ^ swz(b) for disjoint a, b.  Keeps 128-bit accesses of a quarter warp on eight
@@ -82,15 +75,17 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
 }
 
 // Explicit global-space 128-bit / 64-bit accesses (the state pointer comes out of a struct in memory, which
-// the compiler would otherwise treat as a generic address).
+// the compiler would otherwise treat as a generic address).  The loads are `asm volatile`: a plain asm is "pure" to the
+// compiler, which may then hoist it above the condition that guards it (seen: the diagonal-table load speculated with a
+// null table pointer).
 __device__ __forceinline__ double2 ld_state(const double2* p) {
     double2 r;
-    asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ float2 ld_state(const float2* p) {
     float2 r;
-    asm("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void st_state(double2* p, double2 v) {
@@ -101,7 +96,7 @@ __device__ __forceinline__ void st_state(float2* p, float2 v) {
 }
 __device__ __forceinline__ double ld_table(const double* p) {
     double r;
-    asm("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
     return r;
 }
 
@@ -109,10 +104,10 @@ __device__ __forceinline__ double ld_table(const double* p) {
 // bit CB (only the 4 pairs with that bit set are touched); CB < 0: all 8 pairs.  Everything is resolved at compile
 // time so the 8 (4) pair updates are straight-line code the scheduler can interleave (no per-pair predicates).
 template <typename T, int R, int B, int CB>
-__device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
+__device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type m00, const typename Cx<T>::type m01,
+                                            const typename Cx<T>::type m10, const typename Cx<T>::type m11) {
     constexpr int kNReg = 1 << R;
     using C = typename Cx<T>::type;
-    const C m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
 #pragma unroll
     for (int j = 0; j < kNReg; ++j) {
         if (j & (1 << B)) continue;
@@ -139,12 +134,6 @@ __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], c
     }
 }
 
-// dispatch helper: silently ignores (B, CB) combinations that cannot occur for R register bits
-template <typename T, int R, int B, int CB>
-__device__ __forceinline__ void apply_dense_v(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
-    if constexpr (B < R && CB < R && B != CB) apply_dense<T, R, B, CB>(a, m);
-}
-
 template <typename T>
 __device__ __forceinline__ typename Cx<T>::type cmul(typename Cx<T>::type a, typename Cx<T>::type b) {
     typename Cx<T>::type r;
@@ -165,264 +154,368 @@ __device__ __forceinline__ U reg_offset(int j, const U (&off)[R]) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// sweep kernel: grid = (tiles, active batch entries), block = 256 threads, dynamic smem = sweep_smem_bytes<T>()
+// sweep kernel: grid = (tiles >> m_log2, active batch entries), block = 2^(K-R) threads, dynamic smem = sweep_smem_bytes<T, R, K>()
+//
+// Every CTA stages the sweep program of ITS circuit once -- pass records, matrices, one pre-decoded dispatch word per op, the
+// per-pass thread -> tile-slot table -- and then walks 2^m_log2 consecutive tiles with it, so the dependent-load prologue and
+// all per-pass index arithmetic are paid once per CTA instead of once per tile.  Per tile only the operands that live outside
+// the tile (controls / diagonal targets on non-tile qubits) are re-resolved, by one thread per op, into a double-buffered word
+// list; the single CTA barrier per tile that publishes it sits behind the issue of the tile's HBM loads.
 // ---------------------------------------------------------------------------------------------------
+constexpr int kWordStride = kMaxSweepOps + 1;
+constexpr int kMaxInitQubits = 64;
+
+// dispatch word: variant | cpos << 6 | dpos << 11 | dflag << 16 | cb << 17 | tb << 20 | treg << 23
+//   cpos  tile-local position of a thread-bit control; 31 = none (bit 31 of the test word is always set), 30 = an external
+//         control that is 0 for this tile (bit 30 is never set)
+//   dpos  tile-local position of a thread-bit diagonal target; 31 = use dflag (external target, resolved per tile)
+//   cb / tb / treg  register-bit control / register-bit target of the generic controlled diagonal
+template <int R> __host__ __device__ constexpr int v_dense(int B) { return B; }
+template <int R> __host__ __device__ constexpr int v_ctrl(int B, int CB) { return R + B * (R - 1) + (CB < B ? CB : CB - 1); }
+template <int R> __host__ __device__ constexpr int v_diag_out() { return R * R; }
+template <int R> __host__ __device__ constexpr int v_diag_reg(int b) { return R * R + 1 + b; }
+template <int R> __host__ __device__ constexpr int v_diag_gen() { return R * R + 1 + R; }
+
+template <typename T, int R, int K>
+constexpr size_t sweep_smem_bytes() {
+    return sizeof(typename Cx<T>::type) * (size_t(1) << K) + sizeof(T) * 8 * kMaxSweepOps + sizeof(typename Cx<T>::type) * 2 * kMaxInitQubits +
+           sizeof(uint32_t) * kMaxSweepPasses * 8 + sizeof(uint32_t) * 4 * kWordStride + sizeof(qb_pass) * kMaxSweepPasses +
+           sizeof(uint16_t) * kMaxSweepPasses * (size_t(1) << (K - R));
+}
+
+template <typename T, int R>
+__device__ __forceinline__ void apply_op(uint32_t word, uint32_t e_thr, typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
+    static_assert(R == 4, "the dispatch table is written for 2^4 amplitudes per thread");
+    using C = typename Cx<T>::type;
+    constexpr int kNReg = 1 << R;
+    const uint32_t variant = word & 63u;
+    // (matrix entries are read where a case needs them: hoisting the four 128-bit loads above the dispatch costs 16 live
+    //  registers and spills -- measured -6 %)
+#define m00 m[0]
+#define m01 m[1]
+#define m10 m[2]
+#define m11 m[3]
+    auto diag_select = [&]() -> C {  // factor of a diagonal whose target is not a register bit
+        const uint32_t sel = ((e_thr | ((word >> 16) << 31)) >> ((word >> 11) & 31u)) & 1u;
+        return sel ? m11 : m00;
+    };
+    if (variant < 4u) {  // uncontrolled dense ops are most of what runs: two predictable branches instead of the jump table (+2 %)
+        if (variant & 2u) {
+            if (variant & 1u) apply_dense<T, R, 3, -1>(a, m00, m01, m10, m11);
+            else apply_dense<T, R, 2, -1>(a, m00, m01, m10, m11);
+        } else {
+            if (variant & 1u) apply_dense<T, R, 1, -1>(a, m00, m01, m10, m11);
+            else apply_dense<T, R, 0, -1>(a, m00, m01, m10, m11);
+        }
+        return;
+    }
+    switch (variant) {
+#define QB_D(B) case v_dense<R>(B): apply_dense<T, R, B, -1>(a, m00, m01, m10, m11); break;
+#define QB_C(B, CB) case v_ctrl<R>(B, CB): apply_dense<T, R, B, CB>(a, m00, m01, m10, m11); break;
+        QB_D(0) QB_D(1) QB_D(2) QB_D(3)
+        QB_C(0, 1) QB_C(0, 2) QB_C(0, 3)
+        QB_C(1, 0) QB_C(1, 2) QB_C(1, 3)
+        QB_C(2, 0) QB_C(2, 1) QB_C(2, 3)
+        QB_C(3, 0) QB_C(3, 1) QB_C(3, 2)
+#undef QB_D
+#undef QB_C
+        case v_diag_out<R>(): {
+            const C d = diag_select();
+#pragma unroll
+            for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], d);
+            break;
+        }
+        case v_diag_reg<R>(0): case v_diag_reg<R>(1): case v_diag_reg<R>(2): case v_diag_reg<R>(3): {
+            const uint32_t tb = 1u << (variant - uint32_t(v_diag_reg<R>(0)));
+            const C d0 = m00, d1 = m11;
+#pragma unroll
+            for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
+            break;
+        }
+        case v_diag_gen<R>(): {  // diagonal with a register-bit control (rare: transpiled cz / cp / crz)
+            const uint32_t cmask = 1u << ((word >> 17) & 7u);
+            const C d0 = m00, d1 = m11;
+            if (word & (1u << 23)) {
+                const uint32_t tb = 1u << ((word >> 20) & 7u);
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j)
+                    if (j & cmask) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
+            } else {
+                const C d = diag_select();
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j)
+                    if (j & cmask) a[j] = cmul<T>(a[j], d);
+            }
+            break;
+        }
+        default: break;
+    }
+#undef m00
+#undef m01
+#undef m10
+#undef m11
+}
+
 template <typename T, int R, int K, typename Idx>
 __global__ void __launch_bounds__(1 << (K - R), (K <= 11 ? 4 : 2))
-// (K - R <= 8: the scatter tables cover at most 8 thread-index bits)
-sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation) {
+sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation, int m_log2) {
     using C = typename Cx<T>::type;
-    constexpr int kRegBits = R;
-    constexpr int kTileBits = K;
     constexpr int kTileSize = 1 << K;
-    constexpr int kThreadBits = kTileBits - R;
+    constexpr int kThreadBits = K - R;
     constexpr int kThreads = 1 << kThreadBits;
     constexpr int kNReg = 1 << R;
+    constexpr int kAmpShift = sizeof(C) == 16 ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem[];
-    C* tile = reinterpret_cast<C*>(smem);
-    C* s_mat = reinterpret_cast<C*>(smem + sizeof(C) * kTileSize);
-    qb_pass_op* s_ops = reinterpret_cast<qb_pass_op*>(smem + sizeof(C) * kTileSize + sizeof(T) * 8 * kMaxSweepOps);
-    qb_pass* s_pass = reinterpret_cast<qb_pass*>(reinterpret_cast<unsigned char*>(s_ops) + sizeof(qb_pass_op) * kMaxSweepOps);
-    uint32_t* s_word = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_pass) + sizeof(qb_pass) * kMaxSweepPasses);
+    unsigned char* sp = smem;
+    unsigned char* tile_b = sp;                                sp += sizeof(C) * kTileSize;
+    C* s_mat = reinterpret_cast<C*>(sp);                       sp += sizeof(T) * 8 * kMaxSweepOps;
+    C* s_init = reinterpret_cast<C*>(sp);                      sp += sizeof(C) * 2 * kMaxInitQubits;
+    uint32_t* s_so = reinterpret_cast<uint32_t*>(sp);          sp += sizeof(uint32_t) * kMaxSweepPasses * 8;
+    uint32_t* s_word0 = reinterpret_cast<uint32_t*>(sp);       sp += sizeof(uint32_t) * kWordStride;
+    uint32_t* s_ext = reinterpret_cast<uint32_t*>(sp);         sp += sizeof(uint32_t) * kWordStride;
+    uint32_t* s_word = reinterpret_cast<uint32_t*>(sp);        sp += sizeof(uint32_t) * 2 * kWordStride;
+    qb_pass* s_pass = reinterpret_cast<qb_pass*>(sp);          sp += sizeof(qb_pass) * kMaxSweepPasses;
+    uint16_t* s_ethr = reinterpret_cast<uint16_t*>(sp);
     __shared__ qb_sweep s_sweep;
+    __shared__ uint64_t s_gi[2][8];
     __shared__ double s_red[32];
+    __shared__ int s_has_ext;
 
-    const BatchEntry en = entries[blockIdx.y];  // block-uniform copy into registers
-    if (sweep_idx >= en.n_sweeps) return;
+    const BatchEntry& ge = entries[blockIdx.y];
+    if (sweep_idx >= ge.n_sweeps) return;
     const int tid = threadIdx.x;
 
+    // ================= staging (once per CTA) =================
     if (tid < int(sizeof(qb_sweep) / 4))
-        reinterpret_cast<int32_t*>(&s_sweep)[tid] = reinterpret_cast<const int32_t*>(en.sweeps + sweep_idx)[tid];
+        reinterpret_cast<int32_t*>(&s_sweep)[tid] = reinterpret_cast<const int32_t*>(ge.sweeps + sweep_idx)[tid];
+    if (tid == 0) s_has_ext = 0;
     __syncthreads();
     const int pass_begin = s_sweep.pass_begin;
     const int n_pass = s_sweep.pass_end - pass_begin;
     const int op_begin = s_sweep.op_begin;
     const int n_sop = s_sweep.op_end - op_begin;
+    const bool product_start = (sweep_idx == 0) && ge.init_zero && (ge.init_ops != nullptr);
+    const bool zero_start = (sweep_idx == 0) && ge.init_zero && (ge.init_ops == nullptr);
 
-    // tile base index = blockIdx.x scattered over the qubits that are not tile bits
+    for (int i = tid; i < n_pass * int(sizeof(qb_pass) / 4); i += kThreads)
+        reinterpret_cast<int32_t*>(s_pass)[i] = reinterpret_cast<const int32_t*>(ge.passes + pass_begin)[i];
+    {
+        T* s_mat_t = reinterpret_cast<T*>(s_mat);
+        const double* __restrict__ mats = ge.matrices + (size_t(ge.n_ops) + size_t(op_begin)) * 8;
+        for (int i = tid; i < n_sop * 8; i += kThreads) s_mat_t[i] = static_cast<T>(mats[i]);
+        if (product_start) {
+            T* s_init_t = reinterpret_cast<T*>(s_init);
+            const double* __restrict__ iv = ge.matrices + (size_t(ge.n_ops) + size_t(ge.n_pass_ops)) * 8;
+            for (int i = tid; i < 4 * n_eff; i += kThreads) s_init_t[i] = static_cast<T>(iv[i]);
+        }
+        for (int i = tid; i <= n_sop; i += kThreads) {
+            uint32_t w = 0, x = 0xffffu;
+            if (i < n_sop) {
+                const qb_pass_op po = ge.pass_ops[op_begin + i];
+                uint32_t cpos = 31, dpos = 31, cb = 0, tb = 0, treg = 0, variant, extc = 0xff, extt = 0xff;
+                if (po.ctrl_kind == QB_K_THREAD) cpos = po.ctrl_pos;
+                else if (po.ctrl_kind == QB_K_EXT) extc = po.ctrl_pos;
+                const int rcb = (po.ctrl_kind == QB_K_REG) ? int(po.ctrl_pos) : -1;
+                if (po.kind == QB_OP_DENSE) {
+                    const int b = po.tgt_pos;
+                    variant = rcb < 0 ? uint32_t(b) : uint32_t(R + b * (R - 1) + (rcb < b ? rcb : rcb - 1));
+                } else {
+                    if (po.tgt_kind == QB_K_THREAD) dpos = po.tgt_pos;
+                    else if (po.tgt_kind == QB_K_EXT) extt = po.tgt_pos;
+                    if (rcb >= 0) {
+                        variant = uint32_t(v_diag_gen<R>());
+                        cb = uint32_t(rcb);
+                        if (po.tgt_kind == QB_K_REG) treg = 1, tb = po.tgt_pos;
+                    } else if (po.tgt_kind == QB_K_REG) {
+                        variant = uint32_t(v_diag_reg<R>(0)) + po.tgt_pos;
+                    } else {
+                        variant = uint32_t(v_diag_out<R>());
+                    }
+                }
+                w = variant | (cpos << 6) | (dpos << 11) | (cb << 17) | (tb << 20) | (treg << 23);
+                x = extc | (extt << 8);
+                if (x != 0xffffu) s_has_ext = 1;
+            }
+            s_word0[i] = w;
+            s_ext[i] = x;
+        }
+    }
+    __syncthreads();  // pass records visible
+    uint64_t tile_mask = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) tile_mask |= 1ull << s_sweep.tile_qubits[i];
+    for (int p = 0; p < n_pass; ++p) {
+        uint32_t e = 0;
+#pragma unroll
+        for (int b = 0; b < kThreadBits; ++b) e |= ((uint32_t(tid) >> b) & 1u) << s_pass[p].thread_bits[b];
+        s_ethr[p * kThreads + tid] = uint16_t(e);
+    }
+    if (tid < n_pass * R) {
+        const int p = tid / R, i = tid % R;
+        s_so[p * 8 + i] = swz(1u << s_pass[p].reg_bits[i]) << kAmpShift;
+    }
+    if (tid < 2 * R) {
+        const int which = tid / R, i = tid % R;
+        s_gi[which][i] = 1ull << s_sweep.tile_qubits[s_pass[which ? n_pass - 1 : 0].reg_bits[i]];
+    }
+    // this thread's global-index bits in the first (load) and last (store) pass layouts
+    Idx gthr_first = 0, gthr_last = 0;
+#pragma unroll
+    for (int b = 0; b < kThreadBits; ++b) {
+        const Idx bit = Idx((uint32_t(tid) >> b) & 1u);
+        gthr_first |= bit << s_sweep.tile_qubits[s_pass[0].thread_bits[b]];
+        gthr_last |= bit << s_sweep.tile_qubits[s_pass[n_pass - 1].thread_bits[b]];
+    }
+    // product-state start: factor contributed by this thread's own tile bits (constant over the CTA's tiles)
+    C p_thread;
+    p_thread.x = T(1), p_thread.y = T(0);
+    if (product_start) {
+        uint64_t reg_q = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) reg_q |= 1ull << s_sweep.tile_qubits[s_pass[0].reg_bits[i]];
+        for (int i = 0; i < K; ++i) {
+            const int q = s_sweep.tile_qubits[i];
+            if (!((reg_q >> q) & 1ull)) p_thread = cmul<T>(p_thread, s_init[2 * q + int((uint64_t(gthr_first) >> q) & 1ull)]);
+        }
+        if ((ge.index_offset >> n_eff) != 0) p_thread.x = T(0), p_thread.y = T(0);  // rank bits above the local register start in |0>
+    }
+    __syncthreads();
+    const bool has_ext = s_has_ext != 0;
+
+    C* __restrict__ st = reinterpret_cast<C*>(ge.state);
+    const C* __restrict__ src = (sweep_idx == 0 && ge.src_state != nullptr) ? reinterpret_cast<const C*>(ge.src_state) : st;
+    const bool do_expect = fuse_expectation && (sweep_idx == ge.n_sweeps - 1) && (ge.diag_table != nullptr);
+    const double* __restrict__ table = ge.diag_table;
+    const uint64_t index_offset = ge.index_offset;
+    const uint64_t not_tile = ~tile_mask & ((n_eff >= 64) ? ~0ull : ((1ull << n_eff) - 1ull));
+
+    // first tile of this CTA: blockIdx.x << m_log2 scattered over the qubits that are not tile bits
     uint64_t base = 0;
     {
-        uint64_t tile_mask = 0;
-#pragma unroll
-        for (int i = 0; i < kTileBits; ++i) tile_mask |= 1ull << s_sweep.tile_qubits[i];
-        uint64_t t = blockIdx.x;
+        uint64_t t = uint64_t(blockIdx.x) << m_log2;
         for (int q = 0; q < n_eff; ++q)
             if (!((tile_mask >> q) & 1ull)) {
                 base |= (t & 1ull) << q;
                 t >>= 1;
             }
     }
-    const uint64_t gbase = base | en.index_offset;
-    C* __restrict__ st = reinterpret_cast<C*>(en.state);
-    const bool do_expect = fuse_expectation && (sweep_idx == en.n_sweeps - 1) && (en.diag_table != nullptr);
-    const double* __restrict__ table = en.diag_table;
-
-    // Per-pass thread context: where this thread's 2^R amplitudes live in the tile / in global memory.
-    uint32_t e_thr, s_thr, so[kRegBits];
-    uint64_t g_thr, g0, go[kRegBits];
-    Idx i0, gi[kRegBits];
-    auto setup_pass = [&](const qb_pass& ps) {
-        e_thr = 0, g_thr = 0;
-#pragma unroll
-        for (int b = 0; b < kThreadBits; ++b) {
-            const uint32_t bit = (tid >> b) & 1u;
-            const int pos = ps.thread_bits[b];
-            e_thr |= bit << pos;
-            g_thr |= uint64_t(bit) << s_sweep.tile_qubits[pos];
-        }
-        s_thr = swz(e_thr);
-#pragma unroll
-        for (int i = 0; i < kRegBits; ++i) {
-            so[i] = swz(1u << ps.reg_bits[i]);
-            go[i] = 1ull << s_sweep.tile_qubits[ps.reg_bits[i]];
-            gi[i] = Idx(go[i]);
-        }
-        g0 = base | g_thr;
-        i0 = Idx(g0);
-    };
-
-    // ---- first pass: its record comes straight from global memory so that the HBM loads of the tile are in flight
-    //      while the rest of the sweep program (passes, ops, matrices) is staged into shared memory
+    const uint32_t n_iter = 1u << m_log2;
+    double acc = 0.0;
     C a[kNReg];
-    {
-        const qb_pass ps = en.passes[pass_begin];
-        setup_pass(ps);
-        if (sweep_idx == 0 && en.init_zero && en.init_ops != nullptr) {
-            // product-state start: amplitude(k) = prod_q v_q[bit_q(k)], v_q = first column of qubit q's first
-            // gate (or |0>), written per qubit by bind_kernel.  P collects the factors of all index bits shared by this
-            // thread's amplitudes, the register bits are expanded by doubling.
-            const double2* __restrict__ init_vec = reinterpret_cast<const double2*>(en.matrices + (size_t(en.n_ops) + size_t(en.n_pass_ops)) * 8);
-            const uint64_t Wi = gbase | g_thr;
-            uint64_t reg_qubits = 0;
-#pragma unroll
-            for (int i = 0; i < kRegBits; ++i) reg_qubits |= go[i];
-            // the addresses depend only on this thread's index bits: the loads are independent and pipeline freely
-            C Pp[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) Pp[i].x = T(1), Pp[i].y = T(0);
-            for (int q0 = 0; q0 < n_eff; q0 += 4) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = q0 + i;
-                    if (q < n_eff && !((reg_qubits >> q) & 1ull)) {
-                        const double2 v = __ldg(init_vec + 2 * q + int((Wi >> q) & 1ull));
-                        C vv;
-                        vv.x = T(v.x), vv.y = T(v.y);
-                        Pp[i] = cmul<T>(Pp[i], vv);
-                    }
-                }
+
+    for (uint32_t it = 0; it < n_iter; ++it, base = ((base | tile_mask) + 1ull) & not_tile) {
+        const uint64_t gbase = base | index_offset;
+        // ---- per-tile resolution of operands outside the tile (one thread per op)
+        const uint32_t* s_w = s_word0;
+        if (has_ext) {
+            uint32_t* dst = s_word + (it & 1u) * kWordStride;
+            if (tid <= n_sop) {
+                uint32_t w = s_word0[tid];
+                const uint32_t x = s_ext[tid];
+                const uint32_t qc = x & 0xffu, qt = (x >> 8) & 0xffu;
+                if (qc != 0xffu && !((gbase >> qc) & 1ull)) w = (w & ~(31u << 6)) | (30u << 6);
+                if (qt != 0xffu) w |= uint32_t((gbase >> qt) & 1ull) << 16;
+                dst[tid] = w;
             }
-            C P = cmul<T>(cmul<T>(Pp[0], Pp[1]), cmul<T>(Pp[2], Pp[3]));
-            if ((en.index_offset >> n_eff) != 0) P.x = T(0), P.y = T(0);  // rank bits above the local register start in |0>
+            s_w = dst;
+        }
+        // ---- first pass: amplitudes from HBM (or synthesised) straight into registers
+        if (product_start) {
+            C P = p_thread;
+            for (int q = 0; q < n_eff; ++q)
+                if ((not_tile >> q) & 1ull) P = cmul<T>(P, s_init[2 * q + int((base >> q) & 1ull)]);
             a[0] = P;
 #pragma unroll
-            for (int i = 0; i < kRegBits; ++i) {
-                const int q = s_sweep.tile_qubits[ps.reg_bits[i]];
-                const double2 w0 = __ldg(init_vec + 2 * q), w1 = __ldg(init_vec + 2 * q + 1);
-                C v0, v1;
-                v0.x = T(w0.x), v0.y = T(w0.y), v1.x = T(w1.x), v1.y = T(w1.y);
+            for (int i = 0; i < R; ++i) {
+                const int q = 63 - __clzll((long long)s_gi[0][i]);
+                const C v0 = s_init[2 * q], v1 = s_init[2 * q + 1];
 #pragma unroll
                 for (int j = 0; j < (1 << i); ++j) {
                     a[j | (1 << i)] = cmul<T>(a[j], v1);
                     a[j] = cmul<T>(a[j], v0);
                 }
             }
-        } else if (sweep_idx == 0 && en.init_zero) {
-#pragma unroll
-            for (int j = 0; j < kNReg; ++j) {
-                const uint64_t idx = g0 | reg_offset<kRegBits>(j, go);
-                a[j].x = ((idx | en.index_offset) == 0) ? T(1) : T(0);
-                a[j].y = T(0);
-            }
         } else {
-            const C* __restrict__ src = (sweep_idx == 0 && en.src_state != nullptr) ? reinterpret_cast<const C*>(en.src_state) : st;
+            Idx ix[kNReg];
+            ix[0] = Idx(base) | gthr_first;
 #pragma unroll
-            for (int j = 0; j < kNReg; ++j) {
-                const Idx idx = i0 | reg_offset<kRegBits>(j, gi);
-                a[j] = ld_state(src + idx);
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int j = 0; j < (1 << i); ++j) ix[j | (1 << i)] = ix[j] | Idx(s_gi[0][i]);
+            if (zero_start) {
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j) {
+                    a[j].x = ((uint64_t(ix[j]) | index_offset) == 0) ? T(1) : T(0);
+                    a[j].y = T(0);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j) a[j] = ld_state(src + ix[j]);
+            }
+        }
+        // publishes this tile's words; also orders the previous tile's shared-memory reads before this tile's writes
+        __syncthreads();
+
+        for (int p = 0; p < n_pass; ++p) {
+            const bool last = (p == n_pass - 1);
+            const uint32_t e_thr = s_ethr[p * kThreads + tid];
+            const uint32_t sb = swz(e_thr) << kAmpShift;
+            if (p != 0) {
+                uint32_t sx[kNReg];
+                sx[0] = sb;
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+#pragma unroll
+                    for (int j = 0; j < (1 << i); ++j) sx[j | (1 << i)] = sx[j] ^ s_so[p * 8 + i];
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j) a[j] = *reinterpret_cast<const C*>(tile_b + sx[j]);
+            }
+
+            // ---- gates of this pass, applied in registers ----
+            const uint32_t test = e_thr | 0x80000000u;
+            const int o_end = s_pass[p].op_end - op_begin;
+            int o = s_pass[p].op_begin - op_begin;
+            uint32_t word_next = s_w[o];
+            for (; o < o_end; ++o) {
+                const uint32_t word = word_next;
+                word_next = s_w[o + 1];  // prefetch the next dispatch word behind this op's arithmetic
+                if (!((test >> ((word >> 6) & 31u)) & 1u)) continue;
+                apply_op<T, R>(word, e_thr, a, s_mat + o * 4);
+            }
+
+            // ---- store ----
+            if (last) {
+                Idx ix[kNReg];
+                ix[0] = Idx(base) | gthr_last;
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+#pragma unroll
+                    for (int j = 0; j < (1 << i); ++j) ix[j | (1 << i)] = ix[j] | Idx(s_gi[1][i]);
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j) {
+                    st_state(st + ix[j], a[j]);
+                    if (do_expect) acc += (double(a[j].x) * double(a[j].x) + double(a[j].y) * double(a[j].y)) * ld_table(table + ix[j]);
+                }
+            } else {
+                // every thread writes back exactly the shared-memory slots it loaded in this pass: no hazard before the store
+                uint32_t sx[kNReg];
+                sx[0] = sb;
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+#pragma unroll
+                    for (int j = 0; j < (1 << i); ++j) sx[j | (1 << i)] = sx[j] ^ s_so[p * 8 + i];
+#pragma unroll
+                for (int j = 0; j < kNReg; ++j) *reinterpret_cast<C*>(tile_b + sx[j]) = a[j];
+                // the next pass re-reads the tile in its own layout: CTA barrier, unless both passes keep the same tile bits on
+                // the warp-index bits -- then every warp only reads what it wrote itself
+                if (s_pass[p].flags & QB_PASS_WARP_LOCAL) __syncwarp();
+                else __syncthreads();
             }
         }
     }
-
-    // ---- stage the sweep program: all four copies are independent (ranges come from the sweep record, matrices are
-    //      stored in pass-op order by bind_kernel), one barrier publishes them
-    for (int i = tid; i < n_pass * int(sizeof(qb_pass) / 4); i += kThreads)
-        reinterpret_cast<int32_t*>(s_pass)[i] = reinterpret_cast<const int32_t*>(en.passes + pass_begin)[i];
-    for (int i = tid; i < n_sop * int(sizeof(qb_pass_op) / 4); i += kThreads)
-        reinterpret_cast<int32_t*>(s_ops)[i] = reinterpret_cast<const int32_t*>(en.pass_ops + op_begin)[i];
-    {
-        T* s_mat_t = reinterpret_cast<T*>(s_mat);
-        const double* __restrict__ mats = en.matrices + (size_t(en.n_ops) + size_t(op_begin)) * 8;
-        for (int i = tid; i < n_sop * 8; i += kThreads) s_mat_t[i] = static_cast<T>(mats[i]);
-        // pre-decoded dispatch words: variant | ctrl_qubit << 8 | tgt_qubit << 16
-        for (int i = tid; i <= n_sop; i += kThreads) {
-            uint32_t w = 0;
-            if (i < n_sop) {
-                const qb_pass_op po = en.pass_ops[op_begin + i];
-                w = uint32_t(po.variant) | (uint32_t(po.ctrl_qubit) << 8) | (uint32_t(po.tgt_qubit) << 16);
-            }
-            s_word[i] = w;
-        }
-    }
-    __syncthreads();
-
-    for (int p = 0; p < n_pass; ++p) {
-        const qb_pass& ps = s_pass[p];
-        const bool first = (p == 0), last = (p == n_pass - 1);
-        if (!first) {
-            setup_pass(ps);
-#pragma unroll
-            for (int j = 0; j < kNReg; ++j) {
-                const uint32_t si = s_thr ^ reg_offset<kRegBits>(j, so);
-                a[j] = tile[si];
-            }
-        }
-
-        // ---- gates of this pass, applied in registers ----
-        // W = index bits shared by all of this thread's amplitudes: predicates for controls / diagonal targets that
-        // are not register bits are single bit tests on it.
-        const uint64_t W = gbase | g_thr;
-        const int o_end = ps.op_end - op_begin;
-        int o = ps.op_begin - op_begin;
-        uint32_t word_next = s_word[o];
-        for (; o < o_end; ++o) {
-            const uint32_t word = word_next;
-            word_next = s_word[o + 1];  // prefetch the next dispatch word behind this op's arithmetic
-            const uint32_t cq = (word >> 8) & 0xffu;
-            if (cq != 0xffu && !((W >> cq) & 1ull)) continue;
-            const C* m = s_mat + o * 4;
-            switch (word & 0xffu) {
-#define QB_DENSE_CASES(B)                                                    \
-    case 6 * B + 0: apply_dense_v<T, R, B, -1>(a, m); break;                  \
-    case 6 * B + 1: apply_dense_v<T, R, B, 0>(a, m); break;                   \
-    case 6 * B + 2: apply_dense_v<T, R, B, 1>(a, m); break;                   \
-    case 6 * B + 3: apply_dense_v<T, R, B, 2>(a, m); break;                   \
-    case 6 * B + 4: apply_dense_v<T, R, B, 3>(a, m); break;                   \
-    case 6 * B + 5: apply_dense_v<T, R, B, 4>(a, m); break;
-                QB_DENSE_CASES(0)
-                QB_DENSE_CASES(1)
-                QB_DENSE_CASES(2)
-                QB_DENSE_CASES(3)
-                QB_DENSE_CASES(4)
-#undef QB_DENSE_CASES
-                case 32: {  // diagonal, target bit outside the registers: one factor for all amplitudes
-                    const C d = ((W >> ((word >> 16) & 0xffu)) & 1ull) ? m[3] : m[0];
-#pragma unroll
-                    for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], d);
-                    break;
-                }
-                case 33: case 34: case 35: case 36: case 37: {  // diagonal on a register bit
-                    const uint32_t tb = 1u << ((word & 0xffu) - 33u);
-                    const C d0 = m[0], d1 = m[3];
-#pragma unroll
-                    for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
-                    break;
-                }
-                default: {  // generic diagonal with a register-bit control (rare: transpiled cz / cp / crz)
-                    const qb_pass_op po = s_ops[o];
-                    const uint32_t cmask = 1u << po.ctrl_pos;
-                    const C d0 = m[0], d1 = m[3];
-                    if (po.tgt_kind == QB_K_REG) {
-                        const uint32_t tb = 1u << po.tgt_pos;
-#pragma unroll
-                        for (int j = 0; j < kNReg; ++j)
-                            if (j & cmask) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
-                    } else {
-                        const C d = ((W >> po.tgt_qubit) & 1ull) ? d1 : d0;
-#pragma unroll
-                        for (int j = 0; j < kNReg; ++j)
-                            if (j & cmask) a[j] = cmul<T>(a[j], d);
-                    }
-                    break;
-                }
-            }
-        }
-
-        // ---- store ----
-        if (last) {
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < kNReg; ++j) {
-                const Idx idx = i0 | reg_offset<kRegBits>(j, gi);
-                st_state(st + idx, a[j]);
-                if (do_expect) acc += (double(a[j].x) * double(a[j].x) + double(a[j].y) * double(a[j].y)) * ld_table(table + idx);
-            }
-            if (do_expect) {
-                const double total = block_sum(acc, s_red);
-                if (tid == 0) en.partials[blockIdx.x] = total;
-            }
-        } else {
-            // every thread writes back exactly the shared-memory slots it loaded in this pass: no hazard before the store
-#pragma unroll
-            for (int j = 0; j < kNReg; ++j) {
-                const uint32_t si = s_thr ^ reg_offset<kRegBits>(j, so);
-                tile[si] = a[j];
-            }
-            // the next pass re-reads the tile in its own layout: CTA barrier, unless both passes keep the same tile bits on
-            // the warp-index bits -- then every warp only reads what it wrote itself
-            if (ps.flags & QB_PASS_WARP_LOCAL) __syncwarp();
-            else __syncthreads();
-        }
+    if (do_expect) {
+        const double total = block_sum(acc, s_red);
+        if (tid == 0) ge.partials[blockIdx.x] = total;
     }
 }
 

@@ -57,7 +57,7 @@ def test_evqe_circuits_through_planner(n, layers, seed):
     np.testing.assert_allclose(got, want, atol=1e-13)
 
 
-@pytest.mark.parametrize("k,r,low", [(6, 4, 2), (7, 4, 3), (8, 4, 4), (9, 5, 3)])
+@pytest.mark.parametrize("k,r,low", [(6, 4, 2), (7, 4, 3), (8, 4, 4), (9, 4, 3)])
 @pytest.mark.parametrize("n,layers,seed", [(8, 3, 10), (10, 4, 11), (11, 2, 12)])
 def test_small_tiles_exercise_multi_tile_paths(k, r, low, n, layers, seed):
     genome, values = og.random_individual(n, layers, True, seed)
