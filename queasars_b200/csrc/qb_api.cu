@@ -151,7 +151,7 @@ struct qb_context {
     uint64_t default_workspace = uint64_t(8) << 30;  // 80 % of the memory free at creation (cudaMemGetInfo is slow: ask once)
     int64_t launches = 0;
     int64_t next_id = 1;
-    int tiles_log2 = 2;  // tiles per sweep CTA (log2); QB_TILES_LOG2 overrides (measured best: 4 tiles)
+    int tiles_log2 = -1;  // tiles per sweep CTA (log2); -1 = by size (4 tiles, 8 from 2^13 tiles per state on); QB_TILES_LOG2 overrides
     std::mutex mu;
     std::map<int64_t, std::unique_ptr<Plan>> plans;
     std::map<int64_t, std::unique_ptr<Ham>> hams;
@@ -251,7 +251,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         return fail(QB_ERR_INVALID, "Hamiltonian acts on " + std::to_string(ham->n_qubits) + " qubits, circuits on " + std::to_string(b.n_qubits));
     b.fuse_expect = ham && ham->table.p && ham->table_n_eff == b.n_eff && index_offset == 0;  // diagonal part in the last sweep
     b.n_tiles = size_t(1) << (b.n_eff - b.tile_bits);
-    b.tiles_log2 = std::min(ctx->tiles_log2, b.n_eff - b.tile_bits);
+    b.tiles_log2 = std::min(ctx->tiles_log2 >= 0 ? ctx->tiles_log2 : (b.n_eff - b.tile_bits >= 13 ? 3 : 2), b.n_eff - b.tile_bits);
     b.partial_stride = std::max<size_t>(size_t(1) << (b.n_eff - std::min(b.n_eff, qb::kExpTileBits)), std::max<size_t>(b.n_tiles, 1024));
 
     b.order.resize(batch);

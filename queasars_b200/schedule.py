@@ -20,6 +20,7 @@ the circuit's unitaries; reordering commuting gates changes results only at the 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Sequence
 
@@ -34,6 +35,7 @@ MAX_SWEEP_OPS = 96  # csrc/qb_kernels.cuh kMaxSweepOps
 MAX_SWEEP_PASSES = 16  # kMaxSweepPasses
 
 PASS_FLAG_WARP_LOCAL = 1  # qb_pass.flags bit 0
+PREFER_CONTROLS_ON_WARP_BITS = os.environ.get("QB_CTRL_WARP", "1") != "0"  # A/B switch, see DESIGN.md
 
 # position kinds in the encoded program
 K_NONE, K_REG, K_THREAD, K_EXT = 0, 1, 2, 3
@@ -214,10 +216,24 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
         direct = not any(b < low for b in padded[idx])  # lanes 0..low-1 must carry the low tile bits
         return [b for b in range(k) if b not in padded[idx] and not (direct and b < low)]
 
+    def control_positions(idx: int) -> dict[int, int]:
+        """tile positions (outside the pass's register set) that control ops of pass idx -> number of such ops"""
+        count: dict[int, int] = {}
+        for i in members[idx]:
+            c = ops[i].control
+            if c >= 0 and c in pos and pos[c] not in padded[idx]:
+                count[pos[c]] = count.get(pos[c], 0) + 1
+        return count
+
     warp_choice: list[list[int]] = []
     for idx in range(len(padded)):
         cand = warp_candidates(idx)
-        keep = [b for b in (warp_choice[-1] if warp_choice else []) if b in cand]
+        # a control on a lane bit makes the warp run the whole gate with half its lanes masked off; on a warp-index bit
+        # the warps whose control bit is 0 skip the gate: controls go first
+        ctrl = control_positions(idx) if PREFER_CONTROLS_ON_WARP_BITS else {}
+        first = sorted((b for b in cand if b in ctrl), key=lambda b: (-ctrl[b], -b))[:n_warp]
+        cand = [b for b in cand if b not in first]
+        keep = first + [b for b in (warp_choice[-1] if warp_choice else []) if b in cand]
 
         def free_run(b: int) -> int:
             run = 0
