@@ -129,6 +129,7 @@ struct DeviceBatch {
     int64_t total_params = 0, total_ops = 0;
     const Ham* ham = nullptr;
     bool fuse_expect = false;
+    bool skip_final_store = false;  // fused diagonal <H> is the whole result: the last sweep does not write the state back
     size_t n_tiles = 0, partial_stride = 0;
     int tiles_log2 = 0;  // every sweep CTA walks 2^tiles_log2 consecutive tiles (and writes ONE fused-expectation partial)
     int64_t n_state_sweeps = 0, launches_per_run = 0;
@@ -250,6 +251,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
     if (ham && ham->n_qubits != b.n_qubits)
         return fail(QB_ERR_INVALID, "Hamiltonian acts on " + std::to_string(ham->n_qubits) + " qubits, circuits on " + std::to_string(b.n_qubits));
     b.fuse_expect = ham && ham->table.p && ham->table_n_eff == b.n_eff && index_offset == 0;  // diagonal part in the last sweep
+    b.skip_final_store = b.fuse_expect && ham->diagonal && !external_state;
     b.n_tiles = size_t(1) << (b.n_eff - b.tile_bits);
     b.tiles_log2 = std::min(ctx->tiles_log2 >= 0 ? ctx->tiles_log2 : (b.n_eff - b.tile_bits >= 13 ? 3 : 2), b.n_eff - b.tile_bits);
     b.partial_stride = std::max<size_t>(size_t(1) << (b.n_eff - std::min(b.n_eff, qb::kExpTileBits)), std::max<size_t>(b.n_tiles, 1024));
@@ -348,7 +350,7 @@ template <typename T, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, 
         dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(b.active[s]));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s], ctx->stream));
         qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), qb::sweep_smem_bytes<T, R, K>(), ctx->stream>>>(
-            b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? 1 : 0, b.tiles_log2);
+            b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? (b.skip_final_store ? 2 : 1) : 0, b.tiles_log2);
         QB_TRY(check_launch(ctx, "sweep_kernel"));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s + 1], ctx->stream));
     }

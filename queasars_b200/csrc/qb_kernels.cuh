@@ -491,10 +491,17 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                 for (int i = 0; i < R; ++i)
 #pragma unroll
                     for (int j = 0; j < (1 << i); ++j) ix[j | (1 << i)] = ix[j] | Idx(s_gi[1][i]);
+                if (do_expect) {
+                    // fuse_expectation == 2: <H> is all the caller wants (diagonal Hamiltonian): the final state is never read
+                    // again and is not written back
 #pragma unroll
-                for (int j = 0; j < kNReg; ++j) {
-                    st_state(st + ix[j], a[j]);
-                    if (do_expect) acc += (double(a[j].x) * double(a[j].x) + double(a[j].y) * double(a[j].y)) * ld_table(table + ix[j]);
+                    for (int j = 0; j < kNReg; ++j) {
+                        if (fuse_expectation != 2) st_state(st + ix[j], a[j]);
+                        acc += (double(a[j].x) * double(a[j].x) + double(a[j].y) * double(a[j].y)) * ld_table(table + ix[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kNReg; ++j) st_state(st + ix[j], a[j]);
                 }
             } else {
                 // every thread writes back exactly the shared-memory slots it loaded in this pass: no hazard before the store
