@@ -187,6 +187,22 @@ int qb_apply_plan_device(qb_context* ctx, int64_t plan_id, const double* params_
                          void* d_state, int init_zero_state, uint64_t index_offset);
 int qb_expectation_device(qb_context* ctx, int64_t ham_id, int dtype, int n_local, const void* d_state,
                           uint64_t index_offset, double* out_value);
+/* qb_sample on a caller-owned (possibly un-normalised: a shard) device state of 2^n_local amplitudes:
+ * out_indices[s] = searchsorted(cumsum(|psi|^2) / sum, uniforms[s], side='right').  The sharded sampler
+ * (queasars_b200/sharded.py) first picks the shard of every shot from the all-gathered shard masses and hands each
+ * rank its shots with re-scaled uniforms ([upstream] StatevectorSampler / Generator.choice semantics per shard). */
+int qb_sample_device(qb_context* ctx, int dtype, int n_local, const void* d_state, int shots,
+                     const double* uniforms, int64_t* out_indices);
+
+/* Global <-> local qubit swap of a state sharded over `world` = 2^n_global GPUs of one node (BASELINE config C5), fused with its
+ * all-to-all: the calling rank streams its shard `d_state` once and stores every amplitude directly into the rank that owns it
+ * afterwards -- peer_dst[d] is rank d's destination buffer mapped into this process (peer memory over NVLink 5 / NVSwitch, e.g.
+ * torch symmetric memory; peer_dst[rank] = the caller's own spare buffer) -- at its final index: amplitude i with local bits
+ * local_positions[j] = d_j goes to rank d, index i with those bits replaced by the bits of `rank`.  Replaces pack +
+ * ncclAllToAll + unpack.  Asynchronous on the context's stream; the caller synchronises and runs a cross-rank barrier before any
+ * rank touches its destination buffer. */
+int qb_swap_global_p2p(qb_context* ctx, int dtype, int n_local, const void* d_state, void* const* peer_dst, int world, int rank,
+                       int n_global, const int32_t* local_positions);
 
 /* layout self-check for language bindings: sizeof() of the four records above */
 void qb_record_sizes(int32_t out[4]);

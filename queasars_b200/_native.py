@@ -55,6 +55,8 @@ def _declare(lib):
         "qb_batch_stats": [c_void_p, c_int64, P(c_int64), P(c_int64), P(c_int64), P(c_int64)],
         "qb_apply_plan_device": [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_uint64],
         "qb_expectation_device": [c_void_p, c_int64, c_int, c_int, c_void_p, c_uint64, P(c_double)],
+        "qb_sample_device": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
+        "qb_swap_global_p2p": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -74,7 +76,7 @@ EXPORTED_SYMBOLS = (
     "qb_context_set_workspace_limit qb_context_synchronize qb_plan_create qb_plan_destroy qb_plan_set_prefix qb_hamiltonian_create "
     "qb_hamiltonian_destroy qb_hamiltonian_diag_energies qb_evaluate_expectation qb_sample qb_statevector "
     "qb_batch_create qb_batch_set_params qb_batch_run qb_batch_run_timed qb_batch_read qb_batch_destroy qb_batch_stats "
-    "qb_apply_plan_device qb_expectation_device qb_record_sizes"
+    "qb_apply_plan_device qb_expectation_device qb_sample_device qb_swap_global_p2p qb_record_sizes"
 ).split()
 
 

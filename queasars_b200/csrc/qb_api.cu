@@ -1120,4 +1120,68 @@ int qb_expectation_device(qb_context* ctx, int64_t ham_id, int dtype, int n_loca
     return QB_OK;
 }
 
+int qb_sample_device(qb_context* ctx, int dtype, int n_local, const void* d_state, int shots, const double* uniforms, int64_t* out_indices) {
+    if (!ctx || !d_state || !uniforms || !out_indices) return fail(QB_ERR_INVALID, "null argument");
+    if (shots <= 0) return QB_OK;
+    if (n_local < qb::kChunkBits || n_local > 36) return fail(QB_ERR_INVALID, "n_local out of range");
+    if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    const uint64_t size = uint64_t(1) << n_local;
+    const uint64_t n_chunks = size >> qb::kChunkBits;
+    const size_t u_bytes = sizeof(double) * size_t(shots);
+    QB_TRY(ctx->scratch.reserve(2 * u_bytes + sizeof(double) * n_chunks));
+    double* d_uniforms = ctx->scratch.as<double>();
+    int64_t* d_indices = reinterpret_cast<int64_t*>(d_uniforms + shots);
+    double* d_chunks = reinterpret_cast<double*>(d_indices + shots);
+    QB_CUDA(cudaMemcpyAsync(d_uniforms, uniforms, u_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 cgrid(unsigned(std::min<uint64_t>((n_chunks + 7) / 8, 2048)), 1);
+    dim3 sgrid(unsigned((shots + 7) / 8), 1);
+    if (dtype == QB_C128) {
+        qb::chunk_prob_kernel<double><<<cgrid, 256, 0, ctx->stream>>>(static_cast<const double2*>(d_state), size, n_chunks, d_chunks);
+        QB_TRY(check_launch(ctx, "chunk_prob_kernel"));
+        qb::scan_chunks_kernel<<<1, 1024, 0, ctx->stream>>>(d_chunks, n_chunks);
+        QB_TRY(check_launch(ctx, "scan_chunks_kernel"));
+        qb::sample_kernel<double><<<sgrid, 256, 0, ctx->stream>>>(static_cast<const double2*>(d_state), size, d_chunks, n_chunks, size, d_uniforms, shots, d_indices);
+    } else {
+        qb::chunk_prob_kernel<float><<<cgrid, 256, 0, ctx->stream>>>(static_cast<const float2*>(d_state), size, n_chunks, d_chunks);
+        QB_TRY(check_launch(ctx, "chunk_prob_kernel"));
+        qb::scan_chunks_kernel<<<1, 1024, 0, ctx->stream>>>(d_chunks, n_chunks);
+        QB_TRY(check_launch(ctx, "scan_chunks_kernel"));
+        qb::sample_kernel<float><<<sgrid, 256, 0, ctx->stream>>>(static_cast<const float2*>(d_state), size, d_chunks, n_chunks, size, d_uniforms, shots, d_indices);
+    }
+    QB_TRY(check_launch(ctx, "sample_kernel"));
+    QB_CUDA(cudaMemcpyAsync(out_indices, d_indices, u_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QB_OK;
+}
+
+int qb_swap_global_p2p(qb_context* ctx, int dtype, int n_local, const void* d_state, void* const* peer_dst, int world, int rank, int n_global,
+                       const int32_t* local_positions) {
+    if (!ctx || !d_state || !peer_dst || !local_positions) return fail(QB_ERR_INVALID, "null argument");
+    if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
+    if (n_global < 1 || n_global > 4 || world != (1 << n_global) || rank < 0 || rank >= world) return fail(QB_ERR_INVALID, "bad rank layout");
+    if (n_local < n_global || n_local > 36) return fail(QB_ERR_INVALID, "n_local out of range");
+    qb::SwapArgs args{};
+    uint64_t seen = 0;
+    for (int j = 0; j < n_global; ++j) {
+        const int p = local_positions[j];
+        if (p < 0 || p >= n_local || ((seen >> p) & 1)) return fail(QB_ERR_INVALID, "bad local position");
+        seen |= 1ull << p;
+        args.lp[j] = p;
+    }
+    for (int r = 0; r < world; ++r) {
+        if (!peer_dst[r]) return fail(QB_ERR_INVALID, "null peer buffer");
+        args.peer[r] = peer_dst[r];
+    }
+    args.g = n_global, args.rank = rank;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    const uint64_t size = uint64_t(1) << n_local;
+    const int blocks = int(std::min<uint64_t>(uint64_t(ctx->sm_count) * 8, std::max<uint64_t>(1, size / (256 * 4))));
+    if (dtype == QB_C128) qb::swap_p2p_kernel<double2><<<blocks, 256, 0, ctx->stream>>>(static_cast<const double2*>(d_state), args, size);
+    else qb::swap_p2p_kernel<float2><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float2*>(d_state), args, size);
+    return check_launch(ctx, "swap_p2p_kernel");
+}
+
 }  // extern "C"

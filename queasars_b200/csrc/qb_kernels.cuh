@@ -846,6 +846,48 @@ sample_kernel(const typename Cx<T>::type* __restrict__ states, uint64_t state_st
     if (lane == 0) out[blockIdx.y * uint64_t(shots) + shot] = found;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// global <-> local qubit swap of a sharded state, fused with its all-to-all: every rank streams its shard ONCE and stores
+// each amplitude straight into the peer that owns it afterwards (peer-mapped buffers, NVLink 5 / NVSwitch), already at its
+// final position -- no pack pass, no staging buffer, no unpack pass.
+//   element i of rank r (local bits lp = d) -> rank d, element i with the lp bits replaced by r
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxSwapRanks = 16;
+struct SwapArgs {
+    void* peer[kMaxSwapRanks];  // destination buffer of every rank (peer[rank] = own spare buffer)
+    int32_t lp[4];              // local bit positions exchanged with rank bits 0..g-1
+    int32_t g, rank;
+};
+
+template <typename C>
+__global__ void __launch_bounds__(256)
+swap_p2p_kernel(const C* __restrict__ src, SwapArgs args, uint64_t size) {
+    uint64_t lpmask = 0, rbits = 0;
+    for (int j = 0; j < args.g; ++j) {
+        lpmask |= 1ull << args.lp[j];
+        rbits |= uint64_t((args.rank >> j) & 1) << args.lp[j];
+    }
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    constexpr int kUnroll = 4;
+    for (uint64_t i0 = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i0 < size; i0 += stride * kUnroll) {
+        C v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i < size) v[u] = src[i];
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i < size) {
+                int d = 0;
+                for (int j = 0; j < args.g; ++j) d |= int((i >> args.lp[j]) & 1ull) << j;
+                static_cast<C*>(args.peer[d])[(i & ~lpmask) | rbits] = v[u];
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void to_c128_kernel(const typename Cx<T>::type* __restrict__ src, double2* __restrict__ dst, uint64_t size) {
     for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x) {

@@ -256,6 +256,22 @@ class Engine:
         return out.value
 
 
+    def swap_global_p2p(self, dtype, n_local: int, state_ptr: int, peer_ptrs: Sequence[int], rank: int, local_positions: Sequence[int]):
+        """Launch the fused swap + all-to-all kernel (asynchronous on the engine's stream; see include/queasars_b200.h)."""
+        world = len(peer_ptrs)
+        ptrs = np.asarray([int(p) for p in peer_ptrs], dtype=np.uint64)
+        lp = np.asarray(list(local_positions), dtype=np.int32)
+        _native.check(self._lib.qb_swap_global_p2p(self._ctx, _dtype_code(dtype), int(n_local), c_void_p(state_ptr), _native.ptr(ptrs), world, int(rank), len(lp), _native.ptr(lp)))
+
+    def sample_device(self, dtype, n_local: int, state_ptr: int, uniforms: np.ndarray) -> np.ndarray:
+        """searchsorted(cumsum(|psi|^2) / sum, uniforms, side='right') on a caller-owned device state (a shard)."""
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(-1)
+        out = np.empty(uniforms.size, dtype=np.int64)
+        if uniforms.size:
+            _native.check(self._lib.qb_sample_device(self._ctx, _dtype_code(dtype), int(n_local), c_void_p(state_ptr), int(uniforms.size), _native.ptr(uniforms), _native.ptr(out)))
+        return out
+
+
 class ResidentBatch:
     """A fixed list of circuits whose device buffers stay allocated: ``set_params`` (H2D), ``run`` (kernels
     only, asynchronous), ``read`` (D2H + sync).  Used by bench.py and by optimizer inner loops."""

@@ -454,6 +454,13 @@ def test_sharded_api_single_rank(engine):
     e_want = float(np.dot(np.abs(want) ** 2, oq.diagonal_table(n, list(zip(z, c)))))
     assert rel_err(sv.diagonal_expectation(z, c), e_want) < 1e-10
     assert abs(sv.norm_squared() - 1.0) < 1e-12
+    # general Pauli sum and sampling through the device-pointer entry points (qb_expectation_device / qb_sample_device)
+    terms = tfim(n) + [("Y" + "I" * (n - 2) + "X", 0.3)]
+    assert rel_err(sv.expectation(SparsePauliOp.from_list(terms)), oq.estimator_expectation(want, terms)) < 1e-10
+    uniforms = np.random.default_rng(4).random(5000)
+    drawn = sv.sample(len(uniforms), uniforms=uniforms)
+    expect = oq.sample_indices(want, len(uniforms), uniforms=uniforms)  # one rank, identity permutation: same enumeration
+    assert np.count_nonzero(drawn != expect) <= 1
 
 
 def test_prefix_state_reuse_matches_full_evaluation(engine):

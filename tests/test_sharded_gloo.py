@@ -59,6 +59,26 @@ class NumpyShardBackend:
         return total
 
 
+    def pauli_expectation(self, state, x_masks, z_masks, coeffs, n_total, n_local, index_offset):
+        """sum_t Re[c_t <psi|P_t|psi>] restricted to this shard's rows, P|k> = i^{#Y} (-1)^{pc(k&z)} |k^x> (oracle/qiskit_semantics.py)."""
+        arr = state.numpy()
+        idx = np.arange(arr.size, dtype=np.uint64)
+        total = 0.0
+        for x, z, c in zip(x_masks, z_masks, coeffs):
+            assert int(x) >> n_local == 0
+            v = (idx | np.uint64(index_offset)) & np.uint64(z)
+            for s in (32, 16, 8, 4, 2, 1):
+                v ^= v >> np.uint64(s)
+            sign = 1.0 - 2.0 * (v & np.uint64(1)).astype(np.float64)
+            phase = 1j ** bin(int(x) & int(z)).count("1")
+            total += float((c * phase * np.sum(np.conj(arr[idx ^ np.uint64(x)]) * sign * arr)).real)
+        return total
+
+    def sample(self, state, uniforms, n_local):
+        arr = state.numpy()
+        return oq.sample_indices(arr / np.linalg.norm(arr), len(uniforms), uniforms=np.asarray(uniforms))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -83,8 +103,31 @@ def _worker(rank, world, port, n, layers, seed, out):
         coeffs = [float(c) for c in rng.normal(size=6)]
         e_got = sv.diagonal_expectation(z_masks, coeffs)
         e_want = float(np.dot(np.abs(want) ** 2, oq.diagonal_table(n, list(zip(z_masks, coeffs)))))
+        # general Pauli sum: X / Y factors on every qubit in turn (some sit on rank bits -> one more swap), ZZ couplings
+        labels = []
+        for q in range(n):
+            lab = ["I"] * n
+            lab[n - 1 - q] = "X" if q % 2 else "Y"
+            lab[n - 1 - (q + 1) % n] = "Z"
+            labels.append(("".join(lab), float(rng.normal())))
+        labels.append(("Z" * n, 0.25))
+        from queasars_b200.operators import SparsePauliOp
+
+        p_got = sv.expectation(SparsePauliOp.from_list(labels))
+        p_want = oq.estimator_expectation(want, labels)
+        # sampling: the draws must be the inverse-CDF draws in *physical* enumeration order, mapped back to logical indices
+        shots = 2000
+        uniforms = np.random.default_rng(17).random(shots)
+        drawn = sv.sample(shots, uniforms=uniforms)
+        full_phys = sv.gather_physical()
+        phys = oq.sample_indices(full_phys, shots, uniforms=uniforms)
+        expect = np.zeros_like(phys)
+        for q in range(n):
+            expect |= ((phys >> sv.position[q]) & 1) << q
+        mismatches = int(np.count_nonzero(drawn != expect))
+        zero_prob = int(np.count_nonzero(np.abs(want[drawn]) ** 2 == 0.0))
         if rank == 0:
-            out.put((float(np.max(np.abs(got - want))), abs(e_got - e_want), sv.swaps_done, abs(sv.norm_squared() - 1.0)))
+            out.put((float(np.max(np.abs(got - want))), abs(e_got - e_want), sv.swaps_done, abs(sv.norm_squared() - 1.0), abs(p_got - p_want), mismatches, zero_prob))
         else:
             sv.norm_squared()
     finally:
@@ -100,9 +143,10 @@ def test_sharded_state_matches_oracle(world, n, layers, seed):
     [p.start() for p in procs]
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    err, e_err, swaps, norm_err = out.get(timeout=10)
-    assert err < 1e-12 and e_err < 1e-12 and norm_err < 1e-12
+    err, e_err, swaps, norm_err, p_err, mismatches, zero_prob = out.get(timeout=10)
+    assert err < 1e-12 and e_err < 1e-12 and norm_err < 1e-12 and p_err < 1e-12
     assert swaps >= 1  # the circuits do target global qubits
+    assert mismatches <= 2 and zero_prob == 0  # (a re-scaled uniform may land on the other side of a CDF boundary)
 
 
 def test_single_rank_no_swaps():

@@ -67,6 +67,29 @@ t0 = time.perf_counter()
 value = sv.diagonal_expectation(z, c)
 t_exp = time.perf_counter() - t0
 norm = sv.norm_squared()
+# general Pauli sum (transverse-field Ising: X on every qubit, some of them on rank bits) and sampling
+from queasars_b200.operators import SparsePauliOp  # noqa: E402
+
+tfim_terms = []
+for q in range(args.n - 1):
+    lab = ["I"] * args.n
+    lab[args.n - 1 - q] = lab[args.n - 2 - q] = "Z"
+    tfim_terms.append(("".join(lab), -1.0))
+for q in range(args.n):
+    lab = ["I"] * args.n
+    lab[args.n - 1 - q] = "X"
+    tfim_terms.append(("".join(lab), -0.5))
+tfim = SparsePauliOp.from_list(tfim_terms)
+swaps_before = sv.swaps_done
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+tfim_value = sv.expectation(tfim)
+t_tfim = time.perf_counter() - t0
+tfim_swaps = sv.swaps_done - swaps_before
+t0 = time.perf_counter()
+shots = sv.sample(10000, seed=123)
+t_sample = time.perf_counter() - t0
+sampled_energy = float(np.mean([sum(cf * (1 - 2 * (bin(int(s) & int(zm)).count("1") & 1)) for zm, cf in zip(z, c)) for s in shots[:2000]]))
 
 # swap-only timing
 swap_ms = None
@@ -85,21 +108,26 @@ if world > 1:
 if rank == 0:
     out = {"n": args.n, "world": world, "n_local": sv.n_local, "gates": len(gates.ops), "swaps": swaps_in_run, "value": value, "analytic_value": analytic_value,
            "analytic_rel_err": None if analytic_value is None else abs(value - analytic_value) / max(1.0, abs(analytic_value)),
-           "norm_err": abs(norm - 1.0), "run_s": t_run, "expectation_s": t_exp}
+           "norm_err": abs(norm - 1.0), "run_s": t_run, "expectation_s": t_exp, "tfim_value": tfim_value, "tfim_s": t_tfim, "tfim_swaps": tfim_swaps,
+           "sample_10k_s": t_sample, "sampled_energy_2000": sampled_energy, "swap_path": "p2p kernel (peer memory)" if sv._peer_ptrs is not None else "nccl all_to_all"}
     if swap_ms is not None:
         shard_bytes = 16 * (1 << sv.n_local)
         sent = shard_bytes * (world - 1) / world
         out.update(swap_ms=swap_ms, swap_sent_GB=sent / 1e9, swap_GBps_per_dir=sent / (swap_ms * 1e-3) / 1e9,
-                   swap_includes="pack + all_to_all_single + unpack")
+                   swap_includes="one fused kernel (peer stores) + barrier" if sv._peer_ptrs is not None else "pack + all_to_all_single + unpack")
     if args.check and args.n <= 30:
         from queasars_b200.engine import Engine
         from queasars_b200.operators import SparsePauliOp
 
         eng = Engine(local)
         ham = eng.hamiltonian(SparsePauliOp._raw(args.n, [0] * len(z), [int(v) for v in z], [float(v) for v in c]), build_table=False)
-        ref = eng.expectation([eng.compile(gates)], [list(ind.parameter_values)], ham)[0]
+        plan = eng.compile(gates)
+        ref = eng.expectation([plan], [list(ind.parameter_values)], ham)[0]
         out["single_gpu_value"] = float(ref)
         out["rel_err"] = abs(value - ref) / max(1.0, abs(ref))
+        tref = eng.expectation([plan], [list(ind.parameter_values)], eng.hamiltonian(tfim))[0]
+        out["tfim_rel_err"] = abs(tfim_value - tref) / max(1.0, abs(tref))
+        out["sampled_vs_exact_energy"] = [sampled_energy, float(ref)]
     print(json.dumps(out))
 if world > 1:
     dist.destroy_process_group()
