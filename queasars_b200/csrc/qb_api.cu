@@ -1166,7 +1166,7 @@ int qb_swap_global_p2p(qb_context* ctx, int dtype, int n_local, const void* d_st
     uint64_t seen = 0;
     for (int j = 0; j < n_global; ++j) {
         const int p = local_positions[j];
-        if (p < 0 || p >= n_local || ((seen >> p) & 1)) return fail(QB_ERR_INVALID, "bad local position");
+        if (p < 0 || p >= n_local || ((seen >> p) & 1) || (j && p <= local_positions[j - 1])) return fail(QB_ERR_INVALID, "local positions must be distinct, ascending and below n_local");
         seen |= 1ull << p;
         args.lp[j] = p;
     }
@@ -1175,6 +1175,7 @@ int qb_swap_global_p2p(qb_context* ctx, int dtype, int n_local, const void* d_st
         args.peer[r] = peer_dst[r];
     }
     args.g = n_global, args.rank = rank;
+    args.run_bits = std::min(qb::kSwapRunBits, n_local - n_global);
     std::lock_guard<std::mutex> lock(ctx->mu);
     QB_TRY(set_device(ctx));
     const uint64_t size = uint64_t(1) << n_local;
