@@ -109,6 +109,7 @@ struct Ham {
     int table_n_eff = 0;
     // tile-fused evaluation of the non-diagonal groups (expect_tile_kernel); groups that do not fit a tile stay generic
     std::vector<qb::ExpTileSweep> tile_sweeps;
+    std::vector<std::vector<int>> tile_sweep_groups;  // indices into `groups` evaluated by each tile sweep
     std::vector<int> generic_groups;  // indices into `groups`
     DevBuf tile_groups, tile_z, tile_wr, tile_wi;
     int tile_n_eff = 0;
@@ -390,8 +391,31 @@ int expectation_state_t(qb_context* ctx, const Ham& ham, const void* d_state, in
         QB_TRY(check_launch(ctx, "reduce_partials_kernel"));
         first = false;
     }
-    for (const auto& g : ham.groups) {
-        if (g->xmask == 0 && !first) continue;  // diagonal part already taken from the table
+    // non-diagonal groups scheduled into tile sweeps: one read of the state per sweep of groups (usable on a shard as long as
+    // every tile qubit is local; z masks may reach rank bits, they enter through index_offset)
+    std::vector<char> done(ham.groups.size(), 0);
+    if (!ham.tile_sweeps.empty() && n_eff >= qb::kExpTileBits) {
+        const size_t tiles = size_t(1) << (n_eff - qb::kExpTileBits);
+        const size_t smem = sizeof(C) << qb::kExpTileBits;
+        for (size_t si = 0; si < ham.tile_sweeps.size(); ++si) {
+            const auto& sw = ham.tile_sweeps[si];
+            bool local = true;
+            for (int i = 0; i < qb::kExpTileBits; ++i) local = local && sw.tile_qubits[i] < n_eff;
+            if (!local) continue;
+            qb::expect_tile_kernel<T><<<dim3(unsigned(tiles), 1), 256, smem, ctx->stream>>>(
+                static_cast<const C*>(d_state), size, n_eff, index_offset, sw, ham.tile_groups.as<qb::ExpTileGroup>(), ham.tile_z.as<uint64_t>(),
+                ham.tile_wr.as<double>(), ham.tile_wi.as<double>(), d_partials, tiles);
+            QB_TRY(check_launch(ctx, "expect_tile_kernel"));
+            qb::reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(d_partials, int64_t(tiles), int64_t(tiles), d_out, first ? 0 : 1);
+            QB_TRY(check_launch(ctx, "reduce_partials_kernel"));
+            first = false;
+            for (int gi : ham.tile_sweep_groups[si]) done[gi] = 1;
+        }
+    }
+    for (size_t gi = 0; gi < ham.groups.size(); ++gi) {
+        const auto& g = ham.groups[gi];
+        if (done[gi]) continue;
+        if (g->xmask == 0 && !first && ham.table.p && ham.table_n_eff == n_eff && index_offset == 0) continue;  // diagonal part already taken from the table
         if (g->xmask >> n_eff) return fail(QB_ERR_INVALID, "Pauli term flips a qubit outside the local statevector");
         const size_t smem = size_t(g->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double));
         qb::expect_group_kernel<T><<<blocks, 256, smem, ctx->stream>>>(static_cast<const C*>(d_state), size, index_offset, g->xmask,
@@ -830,6 +854,7 @@ int qb_hamiltonian_create(qb_context* ctx, int n_qubits, int n_terms, const uint
             }
             sw.group_end = int(tgroups.size());
             ham->tile_sweeps.push_back(sw);
+            ham->tile_sweep_groups.push_back(chosen);
             pending = rest;
         }
         if (!tgroups.empty()) {
@@ -1110,9 +1135,10 @@ int qb_expectation_device(qb_context* ctx, int64_t ham_id, int dtype, int n_loca
     QB_TRY(set_device(ctx));
     Ham* ham = find_ham(ctx, ham_id);
     if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
-    QB_TRY(ctx->scratch.reserve(sizeof(double) * 2048));
+    const size_t n_part = std::max<size_t>(1024, n_local >= qb::kExpTileBits ? size_t(1) << (n_local - qb::kExpTileBits) : 0);
+    QB_TRY(ctx->scratch.reserve(sizeof(double) * (n_part + 16)));
     double* d_part = ctx->scratch.as<double>();
-    double* d_out = d_part + 1024;
+    double* d_out = d_part + n_part;
     if (dtype == QB_C128) QB_TRY(expectation_state_t<double>(ctx, *ham, d_state, n_local, index_offset, d_part, d_out));
     else QB_TRY(expectation_state_t<float>(ctx, *ham, d_state, n_local, index_offset, d_part, d_out));
     QB_CUDA(cudaMemcpyAsync(out_value, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
