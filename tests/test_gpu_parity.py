@@ -463,6 +463,34 @@ def test_sharded_api_single_rank(engine):
     assert np.count_nonzero(drawn != expect) <= 1
 
 
+@pytest.mark.parametrize("n_local,lp", [(12, [11]), (13, [3, 12]), (14, [0, 5, 13]), (12, [2, 3, 4])])
+def test_fused_swap_kernel_virtual_ranks(engine, n_local, lp):
+    """qb_swap_global_p2p with all "ranks" on one GPU: every rank's kernel stores into the destination buffers of all ranks
+    (here plain device buffers instead of peer-mapped ones); the result must be the bit permutation rank bit j <-> lp[j]."""
+    import torch
+
+    g = len(lp)
+    world = 1 << g
+    rng = np.random.default_rng(n_local + g)
+    full = rng.normal(size=world << n_local) + 1j * rng.normal(size=world << n_local)
+    src = [torch.from_numpy(full[r << n_local : (r + 1) << n_local].copy()).cuda() for r in range(world)]
+    dst = [torch.zeros(1 << n_local, dtype=torch.complex128, device="cuda") for _ in range(world)]
+    torch.cuda.synchronize()
+    for r in range(world):
+        engine.swap_global_p2p("complex128", n_local, src[r].data_ptr(), [d.data_ptr() for d in dst], r, lp)
+    engine.synchronize()
+    got = np.concatenate([d.cpu().numpy() for d in dst])
+    idx = np.arange(world << n_local, dtype=np.int64)
+    swapped = idx.copy()
+    for j, p in enumerate(lp):
+        a, b = (idx >> (n_local + j)) & 1, (idx >> p) & 1
+        swapped &= ~((1 << (n_local + j)) | (1 << p))
+        swapped |= (b << (n_local + j)) | (a << p)
+    want = np.empty_like(full)
+    want[swapped] = full
+    assert np.array_equal(got, want)
+
+
 def test_prefix_state_reuse_matches_full_evaluation(engine):
     """Optimizer pattern (mutation.py:57-81): one layer parameterised, the others bound numerically.  The cached
     prefix state must give the same expectation values as evaluating the whole circuit from |0...0>."""
