@@ -319,8 +319,8 @@ def run_b200(args):
         tot_bytes += float(sweep_bytes_of(batch) * (states.sum() - 0.5 * states[0] - 0.5 * POPULATION) + POPULATION * 8 * (1 << N_QUBITS))
     sweep_bytes = sweep_bytes_of(batch)
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
-    # FP64 side of the roofline: DFMA-class instructions the applied gates need (8 per amplitude for a dense 2x2 gate,
-    # 4 for a controlled one; gates folded into the product-state start or dropped on a |0> control cost nothing) against
+    # FP64 side of the roofline: DFMA-class instructions the applied gates need (8 per amplitude for a dense 2x2 gate, 7 when
+    # its top-left entry is real, half of that for a controlled one; gates folded into the product-state start or dropped on a |0> control cost nothing) against
     # the sustained DFMA issue rate measured on this pool's B200 with tools/fp64_peak.cu (16.9e12 instr/s).
     from queasars_b200 import gate_list as _gl
     from queasars_b200 import schedule as _sc
@@ -329,7 +329,9 @@ def run_b200(args):
     for ind in individuals:
         ops = _gl.from_evqe_individual(ind).ops
         _, remaining = _sc.split_product_prefix(ops, N_QUBITS)
-        dfma += sum((8 if ops[i].control < 0 else 4) for i in remaining) * float(1 << N_QUBITS)
+        # a gate without a global phase (every u / cu3 of an EVQE circuit) has a real top-left entry: 7 instead of 8 per amplitude
+        per_amp = lambda op: 7.0 if (op.gamma.slot < 0 and op.gamma.const == 0.0) else 8.0  # noqa: E731
+        dfma += sum(per_amp(ops[i]) * (1.0 if ops[i].control < 0 else 0.5) for i in remaining) * float(1 << N_QUBITS)
     fp64_peak = 16.9e12
     fp64_rate = dfma / (ms_per_step * 1e-3)
     roofline = {

@@ -103,7 +103,10 @@ __device__ __forceinline__ double ld_table(const double* p) {
 // 2x2 complex matrix on register bit B of the 16 register-resident amplitudes.  CB >= 0: controlled by register
 // bit CB (only the 4 pairs with that bit set are touched); CB < 0: all 8 pairs.  Everything is resolved at compile
 // time so the 8 (4) pair updates are straight-line code the scheduler can interleave (no per-pair predicates).
-template <typename T, int R, int B, int CB>
+// REAL00: the matrix's top-left entry is real (every gate without a global phase, e^{i gamma} = 1: all of EVQE's u / cu3) -- two of
+// the sixteen multiply-adds per pair vanish.  The flag is a property of the plan (gamma identically 0), so it is part of the
+// dispatch word; skipping the two FMAs is bit-identical to executing them with m00.y = +0.
+template <typename T, int R, int B, int CB, bool REAL00 = false>
 __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type m00, const typename Cx<T>::type m01,
                                             const typename Cx<T>::type m10, const typename Cx<T>::type m11) {
     constexpr int kNReg = 1 << R;
@@ -123,8 +126,10 @@ __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], c
         t1 = fma(m01.y, y.x, t1);
         t2 = fma(-m10.y, x.y, t2);
         t3 = fma(m10.y, x.x, t3);
-        t0 = fma(-m00.y, x.y, t0);
-        t1 = fma(m00.y, x.x, t1);
+        if (!REAL00) {
+            t0 = fma(-m00.y, x.y, t0);
+            t1 = fma(m00.y, x.x, t1);
+        }
         t2 = fma(-m11.y, y.y, t2);
         t3 = fma(m11.y, y.x, t3);
         a[j].x = fma(m00.x, x.x, t0);
@@ -166,6 +171,7 @@ constexpr int kWordStride = kMaxSweepOps + 1;
 constexpr int kMaxInitQubits = 64;
 
 // dispatch word: variant | cpos << 6 | dpos << 11 | dflag << 16 | cb << 17 | tb << 20 | treg << 23
+//   variant bit 5 (dense ops): the matrix's top-left entry is real (gamma == 0) -> 14 instead of 16 multiply-adds per pair
 //   cpos  tile-local position of a thread-bit control; 31 = none (bit 31 of the test word is always set), 30 = an external
 //         control that is 0 for this tile (bit 30 is never set)
 //   dpos  tile-local position of a thread-bit diagonal target; 31 = use dflag (external target, resolved per tile)
@@ -199,6 +205,29 @@ __device__ __forceinline__ void apply_op(uint32_t word, uint32_t e_thr, typename
         const uint32_t sel = ((e_thr | ((word >> 16) << 31)) >> ((word >> 11) & 31u)) & 1u;
         return sel ? m11 : m00;
     };
+    if (variant & 32u) {  // dense, real top-left entry (bit 5 of the variant)
+        const uint32_t v = variant & 31u;
+        if (v < 4u) {
+            if (v & 2u) {
+                if (v & 1u) apply_dense<T, R, 3, -1, true>(a, m00, m01, m10, m11);
+                else apply_dense<T, R, 2, -1, true>(a, m00, m01, m10, m11);
+            } else {
+                if (v & 1u) apply_dense<T, R, 1, -1, true>(a, m00, m01, m10, m11);
+                else apply_dense<T, R, 0, -1, true>(a, m00, m01, m10, m11);
+            }
+            return;
+        }
+        switch (v) {
+#define QB_C(B, CB) case v_ctrl<R>(B, CB): apply_dense<T, R, B, CB, true>(a, m00, m01, m10, m11); break;
+            QB_C(0, 1) QB_C(0, 2) QB_C(0, 3)
+            QB_C(1, 0) QB_C(1, 2) QB_C(1, 3)
+            QB_C(2, 0) QB_C(2, 1) QB_C(2, 3)
+            QB_C(3, 0) QB_C(3, 1) QB_C(3, 2)
+#undef QB_C
+            default: break;
+        }
+        return;
+    }
     if (variant < 4u) {  // uncontrolled dense ops are most of what runs: two predictable branches instead of the jump table (+2 %)
         if (variant & 2u) {
             if (variant & 1u) apply_dense<T, R, 3, -1>(a, m00, m01, m10, m11);
@@ -319,6 +348,8 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                 if (po.kind == QB_OP_DENSE) {
                     const int b = po.tgt_pos;
                     variant = rcb < 0 ? uint32_t(b) : uint32_t(R + b * (R - 1) + (rcb < b ? rcb : rcb - 1));
+                    const qb_op_angles& ang = ge.angles[po.op_index];
+                    if (ang.slot[0] < 0 && ang.cnst[0] == 0.0) variant |= 32u;  // gamma == 0: m00 = cos(theta / 2) is real
                 } else {
                     if (po.tgt_kind == QB_K_THREAD) dpos = po.tgt_pos;
                     else if (po.tgt_kind == QB_K_EXT) extt = po.tgt_pos;
