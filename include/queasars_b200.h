@@ -101,6 +101,8 @@ const char* qb_last_error(void);
 void* qb_context_stream(qb_context* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t qb_context_launch_count(qb_context* ctx);
+/* Streaming multiprocessors of the context's device (chunk sizing of the pipelined submission). */
+int qb_context_sm_count(qb_context* ctx);
 /* Upper bound for statevector workspace (bytes); 0 = 80 % of the device memory free at creation. */
 int qb_context_set_workspace_limit(qb_context* ctx, uint64_t bytes);
 int qb_context_synchronize(qb_context* ctx);
@@ -160,6 +162,15 @@ int qb_sample(qb_context* ctx, int batch, const int64_t* plan_ids,
               int shots, const double* uniforms, int64_t* out_indices);
 int qb_statevector(qb_context* ctx, int64_t plan_id, const double* params, int n_params,
                    double* out_re_im /* 2 * 2^n doubles */);
+
+/* Pipelined form of qb_evaluate_expectation for one evaluate_circuits() list handed over in chunks: _submit queues a chunk
+ * (upload, kernels, download into a pinned buffer) and returns without waiting, so the caller can prepare the next chunk's
+ * parameter values (in QUEASARS: Python lists of floats, circuit_evaluation.py:205-207) while the GPU works; _collect waits
+ * for everything queued on this context since the last collect and returns the `total` values in submission order.  All
+ * chunks of one list must be submitted and collected by one thread without other submissions in between. */
+int qb_evaluate_expectation_submit(qb_context* ctx, int batch, const int64_t* plan_ids,
+                                   const double* params, const int64_t* param_offsets, int64_t ham_id);
+int qb_evaluate_expectation_collect(qb_context* ctx, int total, double* out_values);
 
 /* --- resident batches (benchmarks, optimizer inner loops) ---------------------------------------------
  * Same work as qb_evaluate_expectation split into its host<->device and device-only parts so the

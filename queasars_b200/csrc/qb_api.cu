@@ -163,6 +163,14 @@ struct qb_context {
     cudaEvent_t pin_in_done = nullptr;  // last H2D copy out of pin_in
     DevBuf scratch;                     // uniforms / indices / chunk sums / single-state partials
     DeviceBatch oneshot;                // buffers reused by the one-shot entry points (no per-call cudaMalloc)
+    // pipelined submission (qb_evaluate_expectation_submit / _collect): results of queued chunks land here
+    struct PendingChunk {
+        size_t offset;           // first result slot in pin_res
+        std::vector<int> order;  // sorted device position -> index inside the chunk
+    };
+    HostBuf pin_res;
+    std::vector<PendingChunk> pending;
+    size_t pending_results = 0;
 };
 
 namespace {
@@ -581,6 +589,7 @@ int qb_context_destroy(qb_context* ctx) {
     if (ctx->pin_in_done) cudaEventDestroy(ctx->pin_in_done);
     if (ctx->pin_entries_done) cudaEventDestroy(ctx->pin_entries_done);
     ctx->pin_entries.release();
+    ctx->pin_res.release();
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return QB_OK;
@@ -1210,5 +1219,55 @@ int qb_swap_global_p2p(qb_context* ctx, int dtype, int n_local, const void* d_st
     else qb::swap_p2p_kernel<float2><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float2*>(d_state), args, size);
     return check_launch(ctx, "swap_p2p_kernel");
 }
+
+int qb_evaluate_expectation_submit(qb_context* ctx, int batch, const int64_t* plan_ids, const double* params, const int64_t* param_offsets,
+                                   int64_t ham_id) {
+    if (!ctx || !plan_ids || !param_offsets) return fail(QB_ERR_INVALID, "null argument");
+    if (batch <= 0) return QB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    Ham* ham = find_ham(ctx, ham_id);
+    if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
+    Plan* first = find_plan(ctx, plan_ids[0]);
+    if (!first) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[0]));
+    if (size_t(batch) > max_batch_for(ctx, first)) return fail(QB_ERR_MEMORY, "chunk does not fit the statevector workspace");
+    const size_t need = sizeof(double) * (ctx->pending_results + size_t(batch));
+    if (need > ctx->pin_res.cap) {  // grow the pinned result buffer: drain what is in flight first, keep its contents
+        QB_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::vector<double> keep(ctx->pending_results);
+        if (ctx->pending_results) std::memcpy(keep.data(), ctx->pin_res.p, sizeof(double) * ctx->pending_results);
+        QB_TRY(ctx->pin_res.reserve(std::max<size_t>(2 * need, size_t(1) << 16)));
+        if (ctx->pending_results) std::memcpy(ctx->pin_res.p, keep.data(), sizeof(double) * ctx->pending_results);
+    }
+    DeviceBatch& b = ctx->oneshot;
+    QB_TRY(build_batch(ctx, b, batch, plan_ids, ham, nullptr, 1, 0));
+    QB_TRY(batch_upload_params(ctx, b, params, param_offsets));
+    QB_TRY(launch_circuits(ctx, b, nullptr));
+    QB_TRY(launch_expectation(ctx, b));
+    double* dst = static_cast<double*>(ctx->pin_res.p) + ctx->pending_results;
+    QB_CUDA(cudaMemcpyAsync(dst, b.out.p, sizeof(double) * size_t(batch), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->pending.push_back({ctx->pending_results, b.order});
+    ctx->pending_results += size_t(batch);
+    return QB_OK;
+}
+
+int qb_evaluate_expectation_collect(qb_context* ctx, int total, double* out_values) {
+    if (!ctx || (total > 0 && !out_values)) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    const size_t have = ctx->pending_results;
+    std::vector<qb_context::PendingChunk> chunks;
+    chunks.swap(ctx->pending);
+    ctx->pending_results = 0;
+    if (e != cudaSuccess) return fail(QB_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    if (size_t(total) != have) return fail(QB_ERR_INVALID, "collect asked for " + std::to_string(total) + " results, " + std::to_string(have) + " are pending");
+    const double* res = static_cast<const double*>(ctx->pin_res.p);
+    for (const auto& ch : chunks)
+        for (size_t pos = 0; pos < ch.order.size(); ++pos) out_values[ch.offset + size_t(ch.order[pos])] = res[ch.offset + pos];
+    return QB_OK;
+}
+
+int qb_context_sm_count(qb_context* ctx) { return ctx ? ctx->sm_count : 0; }
 
 }  // extern "C"

@@ -10,6 +10,7 @@ cross-thread coalescing on top.
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 import threading
 import weakref
@@ -81,6 +82,9 @@ class Engine:
         self._plan_cache: dict = {}
         self._prefix_bytes = 0
         self._prefix_budget = int(os.environ.get("QB_PREFIX_CACHE_MB", 16384)) << 20  # device memory for cached prefix states
+        self._pipeline = os.environ.get("QB_PIPELINE", "1") != "0"  # two-chunk pipelined submission of large lists (A/B switch)
+        self._submit_lock = threading.Lock()
+        self._sm_count = max(1, int(self._lib.qb_context_sm_count(self._ctx)))
         self._finalizer = weakref.finalize(self, Engine._destroy, self._lib, handle)
         if workspace_limit:
             _native.check(self._lib.qb_context_set_workspace_limit(self._ctx, int(workspace_limit)))
@@ -211,10 +215,47 @@ class Engine:
     def expectation(self, plans: Sequence[PlanHandle], params: Sequence[Sequence[float]], ham: HamiltonianHandle) -> np.ndarray:
         if not plans:
             return np.zeros(0)
-        ids, flat, offsets = self._pack(plans, params)
+        if len(plans) != len(params):
+            raise ValueError(f"{len(plans)} circuits but {len(params)} parameter vectors")
         out = np.empty(len(plans), dtype=np.float64)
-        _native.check(self._lib.qb_evaluate_expectation(self._ctx, len(plans), _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), ham.ham_id, _native.ptr(out)))
+        split = self._pipeline_split(plans, params)
+        if split is None:
+            ids, flat, offsets = self._pack(plans, params)
+            _native.check(self._lib.qb_evaluate_expectation(self._ctx, len(plans), _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), ham.ham_id, _native.ptr(out)))
+            return out
+        # pipelined submission: the GPU starts on the first chunk while the parameter lists of the second are still being
+        # converted to float64 arrays (for a population of Python float lists that conversion is most of the host time)
+        with self._submit_lock:
+            try:
+                for lo, hi in ((0, split), (split, len(plans))):
+                    ids, flat, offsets = self._pack(plans[lo:hi], params[lo:hi])
+                    _native.check(self._lib.qb_evaluate_expectation_submit(self._ctx, hi - lo, _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), ham.ham_id))
+            except Exception:
+                self._lib.qb_evaluate_expectation_collect(self._ctx, 0, None)  # drain whatever was queued
+                raise
+            _native.check(self._lib.qb_evaluate_expectation_collect(self._ctx, len(plans), _native.ptr(out)))
         return out
+
+    def _pipeline_split(self, plans: Sequence[PlanHandle], params) -> Optional[int]:
+        """Size of the first chunk of a two-chunk pipelined submission, or None to submit in one piece.  Worth it when the
+        parameter values arrive as Python sequences (not arrays) and the batch is large; the split point is chosen so that
+        both chunks fill whole waves of sweep CTAs (tiles / 4 CTAs per state, 4 resident CTAs per SM)."""
+        n = len(plans)
+        if n < 8 or not self._pipeline or isinstance(params, np.ndarray) or isinstance(params[0], np.ndarray):
+            return None
+        if sum(p.n_params for p in plans) < 2048:
+            return None
+        n_eff = max(plans[0].n_qubits, self.tile_bits)
+        tiles = 1 << (n_eff - self.tile_bits)
+        ctas = max(1, tiles >> min(3 if n_eff - self.tile_bits >= 13 else 2, n_eff - self.tile_bits))
+        slots = self._sm_count * (4 if self.tile_bits <= 11 else 2)
+
+        def waste(c: int) -> float:
+            w = c * ctas / slots
+            return (math.ceil(w) - w) if w >= 1 else 0.0
+
+        best = min(range(max(2, n // 5), n // 2 + 1), key=lambda c: (round(waste(c) + waste(n - c), 3), c))
+        return best
 
     def sample(self, plans: Sequence[PlanHandle], params: Sequence[Sequence[float]], shots: int, uniforms: np.ndarray) -> np.ndarray:
         if not plans:

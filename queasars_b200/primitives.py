@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import threading
 import weakref
-from typing import Iterable, Optional
+from typing import Iterable, Optional, Sequence
 
 import numpy as np
 
@@ -128,12 +128,14 @@ class _B200Primitive:
             self._ham_cache[key] = (operator, handle)
         return handle
 
-    def _resolve(self, circuit, values) -> tuple[PlanHandle, np.ndarray]:
-        values = np.asarray(values if values is not None else (), dtype=np.float64).reshape(-1)
+    def _resolve(self, circuit, values) -> tuple[PlanHandle, Sequence[float]]:
+        """(plan, parameter values as handed in): the float64 conversion happens chunk by chunk inside the engine's
+        pipelined submission, overlapped with the GPU work of the previous chunk."""
         plan = self._cache.plan_for(circuit)
         if plan is None:
+            values = np.asarray(values if values is not None else (), dtype=np.float64).reshape(-1)
             return self._cache.bound_plan(circuit, values), np.zeros(0)
-        return plan, values
+        return plan, (values if values is not None else ())
 
     def _submit(self, key, payload):
         if self.coalesce:

@@ -463,6 +463,34 @@ def test_sharded_api_single_rank(engine):
     assert np.count_nonzero(drawn != expect) <= 1
 
 
+def test_pipelined_submission_matches_single_call(engine):
+    """Large lists of Python float lists are handed to the engine in two chunks (qb_evaluate_expectation_submit / _collect)
+    so that the second chunk's value conversion overlaps the first chunk's GPU work: same values, same order, and a bad
+    parameter vector in the second chunk still raises cleanly."""
+    n, count = 13, 24
+    terms = random_ising(n, 9)
+    ham = engine.hamiltonian(SparsePauliOp.from_list(terms))
+    plans, params, want = [], [], []
+    for seed in range(count):
+        instr, values, circ = evqe_case(n, 4 + seed % 2, 300 + seed)
+        plans.append(engine.compile(gl.from_circuit(circ)))
+        params.append([float(v) for v in values])
+        if seed % 6 == 0:
+            want.append((seed, oq.estimator_expectation(oq.statevector(instr, n, values), terms)))
+    assert sum(p.n_params for p in plans) >= 2048 and engine._pipeline_split(plans, params) is not None
+    piped = engine.expectation(plans, params, ham)
+    single = engine.expectation(plans, [np.asarray(p) for p in params], ham)  # arrays: submitted in one piece
+    assert engine._pipeline_split(plans, [np.asarray(p) for p in params]) is None
+    assert np.array_equal(piped, single)
+    for i, w in want:
+        assert rel_err(piped[i], w) < 1e-10
+    bad = list(params)
+    bad[-1] = bad[-1][:-1]
+    with pytest.raises(ValueError):
+        engine.expectation(plans, bad, ham)
+    assert np.array_equal(engine.expectation(plans, params, ham), single)  # nothing left pending after the failure
+
+
 @pytest.mark.parametrize("n_local,lp", [(12, [11]), (13, [3, 12]), (14, [0, 5, 13]), (12, [2, 3, 4])])
 def test_fused_swap_kernel_virtual_ranks(engine, n_local, lp):
     """qb_swap_global_p2p with all "ranks" on one GPU: every rank's kernel stores into the destination buffers of all ranks
