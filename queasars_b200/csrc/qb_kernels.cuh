@@ -431,6 +431,17 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             }
     }
     const uint32_t n_iter = 1u << m_log2;
+    // product-state start: the CTA's tiles differ only in the lowest m_log2 non-tile qubits (`var_mask`); the factor of all
+    // other non-tile qubits is the same for every tile of the CTA and joins the per-thread factor once
+    uint64_t var_mask = 0;
+    if (product_start) {
+        uint64_t rest = not_tile;
+        for (int i = 0; i < m_log2 && rest; ++i, rest &= rest - 1ull) var_mask |= rest & (0ull - rest);
+        for (; rest; rest &= rest - 1ull) {
+            const int q = __ffsll((long long)rest) - 1;
+            p_thread = cmul<T>(p_thread, s_init[2 * q + int((base >> q) & 1ull)]);
+        }
+    }
     double acc = 0.0;
     C a[kNReg];
 
@@ -453,8 +464,10 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
         // ---- first pass: amplitudes from HBM (or synthesised) straight into registers
         if (product_start) {
             C P = p_thread;
-            for (int q = 0; q < n_eff; ++q)
-                if ((not_tile >> q) & 1ull) P = cmul<T>(P, s_init[2 * q + int((base >> q) & 1ull)]);
+            for (uint64_t v = var_mask; v; v &= v - 1ull) {
+                const int q = __ffsll((long long)v) - 1;
+                P = cmul<T>(P, s_init[2 * q + int((base >> q) & 1ull)]);
+            }
             a[0] = P;
 #pragma unroll
             for (int i = 0; i < R; ++i) {
