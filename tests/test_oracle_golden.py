@@ -105,6 +105,28 @@ def test_cvar_matches_reference(cvar_golden):
         assert oq.cvar_accumulate(states, case["alpha"]) == pytest.approx(case["expected"], rel=1e-14, abs=1e-14)
 
 
+def test_product_cvar_matches_reference_and_its_vectorised_form(cvar_golden):
+    """queasars_b200.expectation: the loop restatement of _get_expectation and the array version the sampler evaluator uses
+    (no per-entry Python loop) against the fixtures produced by the reference's own function, then against each other on
+    random distributions with ties, early isclose stops and clipped entries."""
+    from queasars_b200 import expectation as ex
+
+    for case in cvar_golden:
+        want = case["expected"]
+        assert ex.lower_tail_expectation(case["probs"], case["values"], case["alpha"]) == pytest.approx(want, rel=1e-14, abs=1e-14)
+        assert ex.lower_tail_expectation_arrays(case["probs"], case["values"], case["alpha"]) == pytest.approx(want, rel=1e-13, abs=1e-13)
+    rng = np.random.default_rng(0)
+    for trial in range(400):
+        n = int(rng.integers(1, 80))
+        counts = rng.integers(1, 40, size=n)
+        probs = counts / counts.sum()
+        values = rng.integers(-4, 5, size=n).astype(float) if trial % 2 else rng.normal(size=n)
+        alpha = float(rng.choice([1.0, 0.5, 0.25, 0.05, 0.999995, float(probs[: max(1, n // 2)].sum())]))
+        a = ex.lower_tail_expectation(probs, values, alpha)
+        b = ex.lower_tail_expectation_arrays(probs, values, alpha)
+        assert b == pytest.approx(a, rel=1e-13, abs=1e-13)
+
+
 # ---------------------------------------------------------------- analytic known answers for the simulator
 def test_u_matrix_and_little_endian():
     # X on qubit 0 of 2 qubits -> |01> = index 1
