@@ -263,6 +263,10 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
     b.skip_final_store = b.fuse_expect && ham->diagonal && !external_state;
     b.n_tiles = size_t(1) << (b.n_eff - b.tile_bits);
     b.tiles_log2 = std::min(ctx->tiles_log2 >= 0 ? ctx->tiles_log2 : (b.n_eff - b.tile_bits >= 13 ? 3 : 2), b.n_eff - b.tile_bits);
+    if (ctx->tiles_log2 < 0) {  // small batches: rather more CTAs than amortised staging -- keep at least two waves of them
+        const size_t slots = size_t(ctx->sm_count) * (b.tile_bits <= 11 ? 4 : 2);
+        while (b.tiles_log2 > 0 && ((b.n_tiles * size_t(batch)) >> b.tiles_log2) < 2 * slots) --b.tiles_log2;
+    }
     b.partial_stride = std::max<size_t>(size_t(1) << (b.n_eff - std::min(b.n_eff, qb::kExpTileBits)), std::max<size_t>(b.n_tiles, 1024));
 
     b.order.resize(batch);
