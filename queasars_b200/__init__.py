@@ -9,13 +9,14 @@ Public surface (mirrors /root/reference/queasars/circuit_evaluation):
 Importing the package never touches CUDA; the first evaluation loads the native library and fails loudly if
 it has not been built or no B200 is present (there is no CPU fallback).
 """
-from .bitstring_evaluation import BitstringEvaluator, BitstringEvaluatorException  # noqa: F401
+from .bitstring_evaluation import BitstringEvaluator, BitstringEvaluatorException, DiagonalEnergyBitstringEvaluator  # noqa: F401
 from .circuit import CU3Gate, Parameter, QuantumCircuit, circuit_to_gate  # noqa: F401
 from .operators import SparsePauliOp  # noqa: F401
 
 __all__ = [
     "BitstringEvaluator",
     "BitstringEvaluatorException",
+    "DiagonalEnergyBitstringEvaluator",
     "QuantumCircuit",
     "Parameter",
     "CU3Gate",

@@ -217,13 +217,44 @@ class B200BitstringCircuitEvaluator(_SamplerEvaluator):
             )
         super().__init__(sampler, sampler_shots, alpha)
         self._initial_state_circuit = initial_state_circuit
+        self._diagonal_op = None
+        if hasattr(bitstring_evaluator, "diagonal_terms"):
+            from .operators import SparsePauliOp
+
+            z, c = bitstring_evaluator.diagonal_terms
+            self._diagonal_op = SparsePauliOp._raw(n, [0] * len(z), [int(v) for v in z], [float(v) for v in c])
 
     def evaluate_circuits(self, circuits: list, parameter_values: list[list[float]]) -> list[float]:
         n = self.n_qubits
-        return [
-            float(ex.expectation_with_bitstring_evaluator(dist, self._bitstring_evaluator, self._alpha, num_bits=n))
-            for dist in self._distributions(circuits, parameter_values)
-        ]
+        vectorised = getattr(self._bitstring_evaluator, "evaluate_states", None)
+        if vectorised is None:  # the reference contract: one call of the user's function per distinct bitstring
+            return [
+                float(ex.expectation_with_bitstring_evaluator(dist, self._bitstring_evaluator, self._alpha, num_bits=n))
+                for dist in self._distributions(circuits, parameter_values)
+            ]
+        # evaluators that can value many basis states at once (DiagonalEnergyBitstringEvaluator: on the device)
+        pairs = [(c, p) for c, p in zip(self._prepend(circuits), parameter_values) if c is not None and p is not None]
+        try:
+            idx = self._sampler.sample_indices([c for c, _ in pairs], [p for _, p in pairs], self._sampler_shots)
+        except (ValueError, TypeError):
+            raise
+        except Exception as exc:
+            raise CircuitEvaluatorException(str(exc)) from exc
+        uniq = [np.unique(row, return_counts=True) for row in idx]
+        if not uniq:
+            return []
+        states_all = np.concatenate([v for v, _ in uniq]).astype(np.uint64)
+        if self._diagonal_op is not None:  # a diagonal energy: all distinct states of the population in one device call
+            ham = self._sampler.hamiltonian_for(self._diagonal_op, build_table=False)
+            values = self._sampler.engine.diag_energies(ham, states_all)
+        else:
+            values = np.asarray(vectorised(states_all), dtype=np.float64)
+        out, pos = [], 0
+        for states, counts in uniq:
+            probs = counts / float(self._sampler_shots)
+            out.append(float(ex.lower_tail_expectation_arrays(probs, values[pos : pos + states.size], self._alpha)))
+            pos += states.size
+        return out
 
     @property
     def n_qubits(self) -> int:

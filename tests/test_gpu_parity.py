@@ -283,7 +283,13 @@ def test_initial_state_circuit(engine):
 
 @pytest.mark.parametrize("alpha", [1.0, 0.5, 0.1])
 def test_sampler_evaluators_match_oracle(jssp_golden, alpha):
-    from queasars_b200 import B200BitstringCircuitEvaluator, B200OperatorSamplerCircuitEvaluator, B200SamplerV2, BitstringEvaluator
+    from queasars_b200 import (
+        B200BitstringCircuitEvaluator,
+        B200OperatorSamplerCircuitEvaluator,
+        B200SamplerV2,
+        BitstringEvaluator,
+        DiagonalEnergyBitstringEvaluator,
+    )
 
     entry = jssp_golden["jssp_5q"]
     n, shots, seed = entry["n_qubits"], 512, 11
@@ -293,6 +299,8 @@ def test_sampler_evaluators_match_oracle(jssp_golden, alpha):
     ev_op = B200OperatorSamplerCircuitEvaluator(sampler, shots, op, alpha=alpha)
     fn = lambda bits: oq.diagonal_energy(int(bits, 2), terms)  # noqa: E731
     ev_bs = B200BitstringCircuitEvaluator(sampler, shots, BitstringEvaluator(n, fn), alpha=alpha)
+    # the same energy as a vectorised evaluator: all distinct sampled states valued in one device call
+    ev_vec = B200BitstringCircuitEvaluator(sampler, shots, DiagonalEnergyBitstringEvaluator(n, entry["z_masks"], entry["coeffs"]), alpha=alpha)
     for s in range(4):
         instr, values, circ = evqe_case(n, 2, 30 + s)
         state = oq.statevector(instr, n, values)
@@ -302,6 +310,7 @@ def test_sampler_evaluators_match_oracle(jssp_golden, alpha):
         want_bs = oq.expectation_with_bitstring_function(dist, n, fn, alpha)
         assert ev_op.evaluate_circuits([circ], [values])[0] == pytest.approx(want_op, rel=1e-10, abs=1e-10)
         assert ev_bs.evaluate_circuits([circ], [values])[0] == pytest.approx(want_bs, rel=1e-10, abs=1e-10)
+        assert ev_vec.evaluate_circuits([circ], [values])[0] == pytest.approx(want_bs, rel=1e-10, abs=1e-10)
     with pytest.raises(ValueError):
         B200OperatorSamplerCircuitEvaluator(sampler, shots, op, alpha=0.0)
     with pytest.raises(ValueError):
