@@ -35,6 +35,9 @@ MAX_SWEEP_OPS = 96  # csrc/qb_kernels.cuh kMaxSweepOps
 MAX_SWEEP_PASSES = 16  # kMaxSweepPasses
 
 PASS_FLAG_WARP_LOCAL = 1  # qb_pass.flags bit 0
+# experiment: let the first / last pass of a sweep hold low (lane) bits in registers -- no empty edge passes, but the HBM
+# accesses of those passes are only partly coalesced (default off)
+ALLOW_LOW_EDGE_PASSES = os.environ.get("QB_ALLOW_LOW_EDGE", "0") != "0"
 PREFER_CONTROLS_ON_WARP_BITS = os.environ.get("QB_CTRL_WARP", "1") != "0"  # A/B switch, see DESIGN.md
 
 # position kinds in the encoded program
@@ -121,7 +124,7 @@ def _select_sweep(ops: Sequence[KernelOp], remaining: list[int], n_eff: int, k: 
     return sorted(tile), chosen, rest
 
 
-def _thread_bit_order(reg: list[int], k: int, low: int, warp_pos: Sequence[int] = ()) -> list[int]:
+def _thread_bit_order(reg: list[int], k: int, low: int, warp_pos: Sequence[int] = (), edge: bool = False) -> list[int]:
     """Which tile-local bit each thread-index bit carries: first the 5 lane bits, then the warp-index bits.
 
     * Passes that touch global memory (no low bit in registers) keep the ``low`` lowest tile bits on lanes 0.. so lanes
@@ -137,8 +140,8 @@ def _thread_bit_order(reg: list[int], k: int, low: int, warp_pos: Sequence[int] 
     rest = [b for b in free if b not in warp]
     while len(warp) < n_warp:  # not enough preferred positions available in this pass: take the highest free ones
         warp.insert(0, rest.pop())
-    if not any(b < low for b in reg):
-        return rest + warp
+    if not any(b < low for b in reg) or edge:
+        return rest + warp  # ascending: the low bits that are not in registers sit on the lowest lanes
     picked: list[int] = []
     for cls in range(3):
         for b in rest:
@@ -152,7 +155,7 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
     k = len(tile_qubits)
     pos = {q: i for i, q in enumerate(tile_qubits)}
     regs: list[list[int]] = [[]]
-    allow_low: list[bool] = [False]
+    allow_low: list[bool] = [ALLOW_LOW_EDGE_PASSES]
     members: list[list[int]] = [[]]
     last_dense: dict[int, int] = {}
     last_any: dict[int, int] = {}
@@ -191,7 +194,7 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
         members[p].append(i)
 
     # the last pass stores straight to global memory: its register bits must avoid the low (lane) bits
-    if any(b < low for b in regs[-1]):
+    if any(b < low for b in regs[-1]) and not ALLOW_LOW_EDGE_PASSES:
         new_pass(False)
     # an empty leading pass is only needed when the next one holds low bits in registers
     if len(regs) > 1 and not members[0] and not any(b < low for b in regs[1]):
@@ -213,7 +216,8 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
     n_warp = max(0, k - r - 5)
 
     def warp_candidates(idx: int) -> list[int]:
-        direct = not any(b < low for b in padded[idx])  # lanes 0..low-1 must carry the low tile bits
+        # lanes 0..low-1 must carry the low tile bits in every pass that touches global memory
+        direct = not any(b < low for b in padded[idx]) or (ALLOW_LOW_EDGE_PASSES and idx in (0, len(padded) - 1))
         return [b for b in range(k) if b not in padded[idx] and not (direct and b < low)]
 
     def control_positions(idx: int) -> dict[int, int]:
@@ -247,8 +251,9 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
         warp_choice.append(sorted((keep + others)[:n_warp]))
 
     passes: list[PassPlan] = []
-    for reg, mem, warp_pos in zip(padded, members, warp_choice):
-        plan = PassPlan(reg_bits=reg, thread_bits=_thread_bit_order(reg, k, low, warp_pos))
+    for idx, (reg, mem, warp_pos) in enumerate(zip(padded, members, warp_choice)):
+        edge = ALLOW_LOW_EDGE_PASSES and idx in (0, len(padded) - 1)
+        plan = PassPlan(reg_bits=reg, thread_bits=_thread_bit_order(reg, k, low, warp_pos, edge))
         for i in mem:
             op = ops[i]
 
