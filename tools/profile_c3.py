@@ -1,5 +1,12 @@
-import cProfile, pstats, sys, os, time
-sys.path.insert(0, "/root/repo")
+"""Where the time of BASELINE config C3 goes (24-qubit TFIM through the estimator evaluator, batch of 4): end-to-end call,
+device-resident run, per-sweep CUDA-event times, cProfile of the host side."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 from queasars_b200 import B200EstimatorV2, B200OperatorCircuitEvaluator
 from queasars_b200 import genome as gn
 pop = gn.random_population(24, 6, 4, True, 0)
