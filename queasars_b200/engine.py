@@ -246,6 +246,8 @@ class Engine:
         if sum(p.n_params for p in plans) < 2048:
             return None
         n_eff = max(plans[0].n_qubits, self.tile_bits)
+        if n_eff > 24:  # large states: the conversion is noise next to the GPU time, and the native call chunks by memory itself
+            return None
         tiles = 1 << (n_eff - self.tile_bits)
         ctas = max(1, tiles >> min(3 if n_eff - self.tile_bits >= 13 else 2, n_eff - self.tile_bits))
         slots = self._sm_count * (4 if self.tile_bits <= 11 else 2)
