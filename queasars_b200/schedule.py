@@ -39,7 +39,7 @@ PASS_FLAG_WARP_LOCAL = 1  # qb_pass.flags bit 0
 # accesses of those passes are only partly coalesced (default off)
 ALLOW_LOW_EDGE_PASSES = os.environ.get("QB_ALLOW_LOW_EDGE", "0") != "0"
 PLAN_TRIALS = int(os.environ.get("QB_PLAN_TRIALS", "48"))  # randomised restarts of the sweep (tile) choice; 0 = greedy only
-PLAN_ACCEPT = 0.8  # probability of accepting a new tile qubit in a randomised trial
+PLAN_ACCEPT = (0.9, 0.8, 0.7)  # probability of accepting a new tile qubit in a randomised trial (cycled over the trials)
 PREFER_CONTROLS_ON_WARP_BITS = os.environ.get("QB_CTRL_WARP", "1") != "0"  # A/B switch, see DESIGN.md
 
 # position kinds in the encoded program
@@ -322,12 +322,12 @@ def plan_circuit(
         init_ops, remaining = [-1] * n_qubits, list(range(len(ops)))
     init_ops = init_ops + [-1] * (n_eff - n_qubits)
 
-    def build(rng) -> list[SweepPlan]:
+    def build(rng, p_accept: float = 1.0) -> list[SweepPlan]:
         todo, out = list(remaining), []
         while todo:
             max_ops = MAX_SWEEP_OPS
             while True:  # the kernel stages at most MAX_SWEEP_OPS matrices / MAX_SWEEP_PASSES pass records per sweep
-                tile_qubits, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, max_ops, rng, PLAN_ACCEPT)
+                tile_qubits, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, max_ops, rng, p_accept)
                 if not chosen:  # an unlucky draw accepted nothing: plain greedy always makes progress
                     tile_qubits, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, max_ops)
                 passes = _plan_passes(ops, chosen, tile_qubits, reg_bits, low_bits)
@@ -338,10 +338,10 @@ def plan_circuit(
             out.append(SweepPlan(tile_qubits, passes))
         return out
 
-    def count_sweeps(rng) -> int:
+    def count_sweeps(rng, p_accept: float) -> int:
         todo, n = list(remaining), 0
         while todo:
-            _, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, MAX_SWEEP_OPS, rng, PLAN_ACCEPT)
+            _, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, MAX_SWEEP_OPS, rng, p_accept)
             if not chosen:
                 _, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, MAX_SWEEP_OPS)
             todo, n = rest, n + 1
@@ -356,13 +356,14 @@ def plan_circuit(
         import zlib
 
         seed0 = zlib.crc32(repr([(op.kind, op.target, op.control) for op in ops]).encode())
-        best_seed, best_n = None, len(sweeps)
+        best_seed, best_n, best_p = None, len(sweeps), 1.0
         for trial in range(PLAN_TRIALS):
-            n = count_sweeps(random.Random(seed0 + trial))
+            p_accept = PLAN_ACCEPT[trial % len(PLAN_ACCEPT)]
+            n = count_sweeps(random.Random(seed0 + trial), p_accept)
             if n < best_n:
-                best_seed, best_n = seed0 + trial, n
+                best_seed, best_n, best_p = seed0 + trial, n, p_accept
         if best_seed is not None:
-            alt = build(random.Random(best_seed))
+            alt = build(random.Random(best_seed), best_p)
             if (len(alt), sum(len(sw.passes) for sw in alt)) < (len(sweeps), sum(len(sw.passes) for sw in sweeps)):
                 sweeps = alt
     if not sweeps:  # empty circuit: one identity sweep so that |0...0> gets materialised
