@@ -34,7 +34,7 @@ extern "C" {
 
 #define QB_TILE_BITS 11     /* default amplitudes per CTA tile = 2^11 (a plan may choose 12) */
 #define QB_MAX_TILE_BITS 12
-#define QB_REG_BITS 4   /* amplitudes per thread = 2^4 */
+#define QB_REG_BITS 4   /* default amplitudes per thread = 2^4 (a plan may choose 3 with 2^11 tiles: 32 warps / SM, measured slower) */
 #define QB_LOW_BITS 4   /* lowest qubits always inside the tile (256 B contiguous runs for c128) */
 
 /* operand-position kinds inside a pass (see queasars_b200/schedule.py) */
@@ -56,7 +56,7 @@ typedef struct qb_sweep {
 } qb_sweep;
 
 typedef struct qb_pass {
-    int32_t reg_bits[7]; /* tile-local bit positions held in registers (first QB_REG_BITS entries used) */
+    int32_t reg_bits[7]; /* tile-local bit positions held in registers (first reg_bits entries used) */
     int32_t flags;       /* bit 0 (QB_PASS_WARP_LOCAL): the next pass keeps the same tile bits on the warp-index bits, so the
                             shared-memory exchange after this pass needs __syncwarp only */
     int32_t op_begin, op_end;

@@ -356,8 +356,7 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
     return QB_OK;
 }
 
-template <typename T, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
-    constexpr int R = QB_REG_BITS;
+template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     for (int s = 0; s < b.max_sweeps; ++s) {
         // every CTA stages its circuit's sweep program once and walks 2^tiles_log2 consecutive tiles with it
         dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(b.active[s]));
@@ -374,18 +373,19 @@ int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     qb::bind_kernel<<<b.batch, 128, 0, ctx->stream>>>(b.entries.as<qb::BatchEntry>());
     QB_TRY(check_launch(ctx, "bind_kernel"));
     // amplitude indices fit 32 bits up to 31 local qubits: cheaper address arithmetic for the common sizes
-#define QB_DISPATCH(K_)                                                                                            \
-    if (b.tile_bits == K_) {                                                                                       \
+#define QB_DISPATCH(R_, K_)                                                                                        \
+    if (b.reg_bits == R_ && b.tile_bits == K_) {                                                                   \
         if (b.n_eff <= 31)                                                                                         \
-            return b.dtype == QB_C128 ? launch_sweeps_t<double, K_, uint32_t>(ctx, b, events)                      \
-                                      : launch_sweeps_t<float, K_, uint32_t>(ctx, b, events);                      \
-        return b.dtype == QB_C128 ? launch_sweeps_t<double, K_, uint64_t>(ctx, b, events)                          \
-                                  : launch_sweeps_t<float, K_, uint64_t>(ctx, b, events);                          \
+            return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_, uint32_t>(ctx, b, events)                  \
+                                      : launch_sweeps_t<float, R_, K_, uint32_t>(ctx, b, events);                  \
+        return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_, uint64_t>(ctx, b, events)                      \
+                                  : launch_sweeps_t<float, R_, K_, uint64_t>(ctx, b, events);                      \
     }
-    QB_DISPATCH(11)
-    QB_DISPATCH(12)
+    QB_DISPATCH(4, 11)
+    QB_DISPATCH(4, 12)
+    QB_DISPATCH(3, 11)
 #undef QB_DISPATCH
-    return fail(QB_ERR_INVALID, "unsupported tile bit count");
+    return fail(QB_ERR_INVALID, "unsupported tile / register bit combination");
 }
 
 // expectation of one resident state with the generic (non-fused) kernels; result accumulated into d_out[0]
@@ -569,13 +569,14 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     }
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_in_done, cudaEventDisableTiming));
     QB_CUDA(cudaEventCreateWithFlags(&ctx->pin_entries_done, cudaEventDisableTiming));
-#define QB_CONFIGURE(K_)                                                                                                \
-    QB_TRY(configure_kernel(qb::sweep_kernel<double, QB_REG_BITS, K_, uint32_t>, qb::sweep_smem_bytes<double, QB_REG_BITS, K_>())); \
-    QB_TRY(configure_kernel(qb::sweep_kernel<float, QB_REG_BITS, K_, uint32_t>, qb::sweep_smem_bytes<float, QB_REG_BITS, K_>()));   \
-    QB_TRY(configure_kernel(qb::sweep_kernel<double, QB_REG_BITS, K_, uint64_t>, qb::sweep_smem_bytes<double, QB_REG_BITS, K_>())); \
-    QB_TRY(configure_kernel(qb::sweep_kernel<float, QB_REG_BITS, K_, uint64_t>, qb::sweep_smem_bytes<float, QB_REG_BITS, K_>()));
-    QB_CONFIGURE(11)
-    QB_CONFIGURE(12)
+#define QB_CONFIGURE(R_, K_)                                                                                            \
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, R_, K_, uint32_t>, qb::sweep_smem_bytes<double, R_, K_>())); \
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_, uint32_t>, qb::sweep_smem_bytes<float, R_, K_>()));   \
+    QB_TRY(configure_kernel(qb::sweep_kernel<double, R_, K_, uint64_t>, qb::sweep_smem_bytes<double, R_, K_>())); \
+    QB_TRY(configure_kernel(qb::sweep_kernel<float, R_, K_, uint64_t>, qb::sweep_smem_bytes<float, R_, K_>()));
+    QB_CONFIGURE(4, 11)
+    QB_CONFIGURE(4, 12)
+    QB_CONFIGURE(3, 11)
 #undef QB_CONFIGURE
     if (const char* e = std::getenv("QB_TILES_LOG2")) ctx->tiles_log2 = std::max(0, std::atoi(e));
     *out = ctx.release();
@@ -624,7 +625,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     if (n_qubits < 1 || n_qubits > 40) return fail(QB_ERR_INVALID, "n_qubits out of range");
     if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
     if (n_sweeps < 1 || n_passes < 1) return fail(QB_ERR_INVALID, "a plan needs at least one sweep with one pass");
-    if (reg_bits != QB_REG_BITS) return fail(QB_ERR_INVALID, "reg_bits must be 4");
+    if (reg_bits != QB_REG_BITS && !(reg_bits == 3 && tile_bits == 11)) return fail(QB_ERR_INVALID, "reg_bits must be 4 (or 3 with 2^11 tiles)");
     const int thread_bits = tile_bits - reg_bits;
     if (tile_bits != 11 && tile_bits != 12) return fail(QB_ERR_INVALID, "tile_bits must be 11 or 12");
     const int n_eff = std::max(n_qubits, tile_bits);

@@ -189,101 +189,99 @@ constexpr size_t sweep_smem_bytes() {
            sizeof(uint16_t) * kMaxSweepPasses * (size_t(1) << (K - R));
 }
 
+// apply_dense for a (B, CB) pair that may not exist for this R (keeps the case lists below uniform)
+template <typename T, int R, int B, int CB, bool REAL00>
+__device__ __forceinline__ void dense_if(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
+    if constexpr (B < R && CB < R && B != CB) apply_dense<T, R, B, CB, REAL00>(a, m[0], m[1], m[2], m[3]);
+}
+
+// uncontrolled dense gate on register bit v (< R): two predictable branches
+template <typename T, int R, bool REAL00>
+__device__ __forceinline__ void dense_by_bit(uint32_t v, typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
+    if (v & 2u) {
+        if constexpr (R > 3) {
+            if (v & 1u) dense_if<T, R, 3, -1, REAL00>(a, m);
+            else dense_if<T, R, 2, -1, REAL00>(a, m);
+        } else {
+            dense_if<T, R, 2, -1, REAL00>(a, m);
+        }
+    } else {
+        if (v & 1u) dense_if<T, R, 1, -1, REAL00>(a, m);
+        else dense_if<T, R, 0, -1, REAL00>(a, m);
+    }
+}
+
+// register-controlled dense gate: c = v - R enumerates (B, CB) as B * (R - 1) + k with CB = the k-th register bit other than B;
+// combinations that do not exist for this R get labels that never match
+template <int R> __host__ __device__ constexpr int ctrl_label(int B, int k) { return (B < R && k < R - 1) ? B * (R - 1) + k : 100 + 4 * B + k; }
+
+template <typename T, int R, bool REAL00>
+__device__ __forceinline__ void ctrl_by_code(uint32_t c, typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
+    switch (c) {
+#define QB_C(B, K_) case ctrl_label<R>(B, K_): dense_if<T, R, B, (K_ < B ? K_ : K_ + 1), REAL00>(a, m); break;
+        QB_C(0, 0) QB_C(0, 1) QB_C(0, 2)
+        QB_C(1, 0) QB_C(1, 1) QB_C(1, 2)
+        QB_C(2, 0) QB_C(2, 1) QB_C(2, 2)
+        QB_C(3, 0) QB_C(3, 1) QB_C(3, 2)
+#undef QB_C
+        default: break;
+    }
+}
+
 template <typename T, int R>
 __device__ __forceinline__ void apply_op(uint32_t word, uint32_t e_thr, typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
-    static_assert(R == 4, "the dispatch table is written for 2^4 amplitudes per thread");
+    static_assert(R == 3 || R == 4, "2^3 or 2^4 amplitudes per thread");
     using C = typename Cx<T>::type;
     constexpr int kNReg = 1 << R;
     const uint32_t variant = word & 63u;
     // (matrix entries are read where a case needs them: hoisting the four 128-bit loads above the dispatch costs 16 live
     //  registers and spills -- measured -6 %)
-#define m00 m[0]
-#define m01 m[1]
-#define m10 m[2]
-#define m11 m[3]
     auto diag_select = [&]() -> C {  // factor of a diagonal whose target is not a register bit
         const uint32_t sel = ((e_thr | ((word >> 16) << 31)) >> ((word >> 11) & 31u)) & 1u;
-        return sel ? m11 : m00;
+        return sel ? m[3] : m[0];
     };
     // The common cases are reached by predictable branches instead of the jump table (+2 %), the commonest first: an
     // uncontrolled dense gate with a real top-left entry (bit 5 of the variant) -- every `u` of an EVQE circuit.
-    if ((variant ^ 32u) < 4u) {
-        if (variant & 2u) {
-            if (variant & 1u) apply_dense<T, R, 3, -1, true>(a, m00, m01, m10, m11);
-            else apply_dense<T, R, 2, -1, true>(a, m00, m01, m10, m11);
-        } else {
-            if (variant & 1u) apply_dense<T, R, 1, -1, true>(a, m00, m01, m10, m11);
-            else apply_dense<T, R, 0, -1, true>(a, m00, m01, m10, m11);
-        }
+    if ((variant ^ 32u) < uint32_t(R)) {
+        dense_by_bit<T, R, true>(variant & 3u, a, m);
         return;
     }
     if (variant & 32u) {  // controlled dense gate with a real top-left entry
-        switch (variant & 31u) {
-#define QB_C(B, CB) case v_ctrl<R>(B, CB): apply_dense<T, R, B, CB, true>(a, m00, m01, m10, m11); break;
-            QB_C(0, 1) QB_C(0, 2) QB_C(0, 3)
-            QB_C(1, 0) QB_C(1, 2) QB_C(1, 3)
-            QB_C(2, 0) QB_C(2, 1) QB_C(2, 3)
-            QB_C(3, 0) QB_C(3, 1) QB_C(3, 2)
-#undef QB_C
-            default: break;
-        }
+        ctrl_by_code<T, R, true>((variant & 31u) - uint32_t(R), a, m);
         return;
     }
-    if (variant < 4u) {  // uncontrolled dense gate with a global phase
-        if (variant & 2u) {
-            if (variant & 1u) apply_dense<T, R, 3, -1>(a, m00, m01, m10, m11);
-            else apply_dense<T, R, 2, -1>(a, m00, m01, m10, m11);
+    if (variant < uint32_t(R)) {  // uncontrolled dense gate with a global phase
+        dense_by_bit<T, R, false>(variant, a, m);
+        return;
+    }
+    if (variant < uint32_t(v_diag_out<R>())) {
+        ctrl_by_code<T, R, false>(variant - uint32_t(R), a, m);
+        return;
+    }
+    if (variant == uint32_t(v_diag_out<R>())) {
+        const C d = diag_select();
+#pragma unroll
+        for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], d);
+    } else if (variant < uint32_t(v_diag_gen<R>())) {
+        const uint32_t tb = 1u << (variant - uint32_t(v_diag_reg<R>(0)));
+        const C d0 = m[0], d1 = m[3];
+#pragma unroll
+        for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
+    } else if (variant == uint32_t(v_diag_gen<R>())) {  // diagonal with a register-bit control (rare: transpiled cz / cp / crz)
+        const uint32_t cmask = 1u << ((word >> 17) & 7u);
+        const C d0 = m[0], d1 = m[3];
+        if (word & (1u << 23)) {
+            const uint32_t tb = 1u << ((word >> 20) & 7u);
+#pragma unroll
+            for (int j = 0; j < kNReg; ++j)
+                if (j & cmask) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
         } else {
-            if (variant & 1u) apply_dense<T, R, 1, -1>(a, m00, m01, m10, m11);
-            else apply_dense<T, R, 0, -1>(a, m00, m01, m10, m11);
-        }
-        return;
-    }
-    switch (variant) {
-#define QB_D(B) case v_dense<R>(B): apply_dense<T, R, B, -1>(a, m00, m01, m10, m11); break;
-#define QB_C(B, CB) case v_ctrl<R>(B, CB): apply_dense<T, R, B, CB>(a, m00, m01, m10, m11); break;
-        QB_D(0) QB_D(1) QB_D(2) QB_D(3)
-        QB_C(0, 1) QB_C(0, 2) QB_C(0, 3)
-        QB_C(1, 0) QB_C(1, 2) QB_C(1, 3)
-        QB_C(2, 0) QB_C(2, 1) QB_C(2, 3)
-        QB_C(3, 0) QB_C(3, 1) QB_C(3, 2)
-#undef QB_D
-#undef QB_C
-        case v_diag_out<R>(): {
             const C d = diag_select();
 #pragma unroll
-            for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], d);
-            break;
+            for (int j = 0; j < kNReg; ++j)
+                if (j & cmask) a[j] = cmul<T>(a[j], d);
         }
-        case v_diag_reg<R>(0): case v_diag_reg<R>(1): case v_diag_reg<R>(2): case v_diag_reg<R>(3): {
-            const uint32_t tb = 1u << (variant - uint32_t(v_diag_reg<R>(0)));
-            const C d0 = m00, d1 = m11;
-#pragma unroll
-            for (int j = 0; j < kNReg; ++j) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
-            break;
-        }
-        case v_diag_gen<R>(): {  // diagonal with a register-bit control (rare: transpiled cz / cp / crz)
-            const uint32_t cmask = 1u << ((word >> 17) & 7u);
-            const C d0 = m00, d1 = m11;
-            if (word & (1u << 23)) {
-                const uint32_t tb = 1u << ((word >> 20) & 7u);
-#pragma unroll
-                for (int j = 0; j < kNReg; ++j)
-                    if (j & cmask) a[j] = cmul<T>(a[j], (j & tb) ? d1 : d0);
-            } else {
-                const C d = diag_select();
-#pragma unroll
-                for (int j = 0; j < kNReg; ++j)
-                    if (j & cmask) a[j] = cmul<T>(a[j], d);
-            }
-            break;
-        }
-        default: break;
     }
-#undef m00
-#undef m01
-#undef m10
-#undef m11
 }
 
 template <typename T, int R, int K, typename Idx>

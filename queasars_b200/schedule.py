@@ -407,7 +407,7 @@ def _predecode(po: PassOp, tile_qubits: Sequence[int]) -> tuple[int, int, int]:
 
 def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
     """-> (sweeps, passes, pass_ops, op_angles, init_ops) arrays."""
-    assert plan.tile_bits <= 16 and plan.reg_bits == REG_BITS
+    assert plan.tile_bits <= 16 and plan.reg_bits in (3, REG_BITS)
     sweeps = np.zeros(len(plan.sweeps), dtype=SWEEP_DTYPE)
     passes = np.zeros(plan.n_passes, dtype=PASS_DTYPE)
     pass_ops = np.zeros(max(1, sum(s.n_ops for s in plan.sweeps)), dtype=PASSOP_DTYPE)
