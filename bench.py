@@ -61,12 +61,16 @@ class ClockSampler:
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     )
 
-    def __init__(self, device_index: int):
+    def __init__(self, device_index: int, enabled: bool = True):
+        # one sampler per job (rank 0): eight nvidia-smi processes starting at once take longer to come up than a timed region lasts
         self.device_index = device_index
+        self.enabled = enabled
         self.proc = None
         self.path = None
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -89,8 +93,10 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        if self.proc is None or not self.path:
+        if not self.enabled:
             return None
+        if self.proc is None or not self.path:
+            return self.single_sample()
         sm, smax, reasons = [], [], set()
         try:
             for line in open(self.path):
@@ -108,8 +114,19 @@ class ClockSampler:
         except Exception:
             return None
         if not sm:
-            return None
+            return self.single_sample()
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def single_sample(self):
+        """Fallback when the looping nvidia-smi produced no line inside the (short) timed region: one query right after it."""
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device_index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            parts = [p.strip() for p in out.split(",")]
+            reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]) if v.lower().startswith("active")]
+            return {"sm_mhz": float(parts[1]), "sm_max_mhz": float(parts[2]), "reasons": sorted(reasons), "samples": 0, "note": "sampled right after the timed region"}
+        except Exception:
+            return None
 
 
 def build_workload(n_qubits: int, layers: int, population: int, seed: int):
@@ -275,7 +292,7 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = engine.launch_count
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
         ev0.record(stream)
         for _ in range(args.steps):
             batch.run()
