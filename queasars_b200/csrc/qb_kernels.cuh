@@ -7,7 +7,9 @@
 //   diag_table_kernel   K3     E(k) = sum_t c_t (-1)^{popcount(k & z_t)}
 //   expect_table_kernel K3     sum_k |psi_k|^2 E(k)
 //   expect_group_kernel K4     Re sum_k psi_k conj(psi_{k^x}) W_x(k) for one x-mask group of a Pauli sum
+//   expect_tile_kernel  K4     the same for all groups that fit one 2^11 tile: one read of the state per tile sweep
 //   chunk_prob_kernel / scan_chunks_kernel / sample_kernel   K5  prefix-sum CDF sampling
+//   swap_p2p_kernel            global <-> local qubit swap of a sharded state fused with its all-to-all (peer-memory stores)
 //
 // What the arithmetic follows ([upstream] = un-vendored qiskit 2.4.2, see oracle/qiskit_semantics.py):
 //   gate matrices   UGate / CU3Gate as emitted by evqe/quantum_circuit/quantum_gate.py:96-102, 157-165
