@@ -39,6 +39,7 @@ PASS_FLAG_WARP_LOCAL = 1  # qb_pass.flags bit 0
 # accesses of those passes are only partly coalesced (default off)
 ALLOW_LOW_EDGE_PASSES = os.environ.get("QB_ALLOW_LOW_EDGE", "0") != "0"
 PLAN_TRIALS = int(os.environ.get("QB_PLAN_TRIALS", "48"))  # randomised restarts of the sweep (tile) choice; 0 = greedy only
+PLAN_FULL_BUILDS = int(os.environ.get("QB_PLAN_FULL_BUILDS", "3"))  # how many of the best draws are planned in full (passes) before the winner is chosen
 PLAN_ACCEPT = (0.9, 0.8, 0.7)  # probability of accepting a new tile qubit in a randomised trial (cycled over the trials)
 PREFER_CONTROLS_ON_WARP_BITS = os.environ.get("QB_CTRL_WARP", "1") != "0"  # A/B switch, see DESIGN.md
 
@@ -356,15 +357,22 @@ def plan_circuit(
         import zlib
 
         seed0 = zlib.crc32(repr([(op.kind, op.target, op.control) for op in ops]).encode())
-        best_seed, best_n, best_p = None, len(sweeps), 1.0
+        best_n, best = len(sweeps), []  # draws that reach the smallest sweep count: (seed, p_accept)
         for trial in range(PLAN_TRIALS):
             p_accept = PLAN_ACCEPT[trial % len(PLAN_ACCEPT)]
             n = count_sweeps(random.Random(seed0 + trial), p_accept)
             if n < best_n:
-                best_seed, best_n, best_p = seed0 + trial, n, p_accept
-        if best_seed is not None:
-            alt = build(random.Random(best_seed), best_p)
-            if (len(alt), sum(len(sw.passes) for sw in alt)) < (len(sweeps), sum(len(sw.passes) for sw in sweeps)):
+                best_n, best = n, []
+            if n == best_n and len(best) < PLAN_FULL_BUILDS:
+                best.append((seed0 + trial, p_accept))
+
+        def cost(candidate: list[SweepPlan]) -> tuple[int, int]:
+            return len(candidate), sum(len(sw.passes) for sw in candidate)
+
+        # among the draws with the fewest sweeps the one with the fewest passes (= shared-memory exchanges) wins
+        for seed, p_accept in best:
+            alt = build(random.Random(seed), p_accept)
+            if cost(alt) < cost(sweeps):
                 sweeps = alt
     if not sweeps:  # empty circuit: one identity sweep so that |0...0> gets materialised
         tile_qubits = list(range(tile_bits))
