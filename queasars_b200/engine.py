@@ -65,6 +65,24 @@ def operator_terms(operator):
     return op.num_qubits, x, z, c
 
 
+def pipeline_split_point(n: int, n_eff: int, tile_bits: int, sm_count: int) -> Optional[int]:
+    """First-chunk size of the two-chunk pipelined submission of ``n`` evaluations of ``n_eff``-qubit states: the split (between
+    a fifth and half of the list) that wastes the fewest partially filled waves of sweep CTAs -- a state contributes
+    tiles / 4 CTAs (tiles / 8 from 2^13 tiles on), an SM holds 4 of them (2 with 2^12-amplitude tiles).  None: do not split
+    (large states: the value conversion is noise next to the GPU time and the native call chunks by memory itself)."""
+    if n < 8 or n_eff > 24:
+        return None
+    tiles = 1 << (n_eff - tile_bits)
+    ctas = max(1, tiles >> min(3 if n_eff - tile_bits >= 13 else 2, n_eff - tile_bits))
+    slots = sm_count * (4 if tile_bits <= 11 else 2)
+
+    def waste(c: int) -> float:
+        w = c * ctas / slots
+        return (math.ceil(w) - w) if w >= 1 else 0.0
+
+    return min(range(max(2, n // 5), n // 2 + 1), key=lambda c: (round(waste(c) + waste(n - c), 3), c))
+
+
 class Engine:
     """One native context (one CUDA device, one stream).  Thread-safe."""
 
@@ -245,19 +263,7 @@ class Engine:
             return None
         if sum(p.n_params for p in plans) < 2048:
             return None
-        n_eff = max(plans[0].n_qubits, self.tile_bits)
-        if n_eff > 24:  # large states: the conversion is noise next to the GPU time, and the native call chunks by memory itself
-            return None
-        tiles = 1 << (n_eff - self.tile_bits)
-        ctas = max(1, tiles >> min(3 if n_eff - self.tile_bits >= 13 else 2, n_eff - self.tile_bits))
-        slots = self._sm_count * (4 if self.tile_bits <= 11 else 2)
-
-        def waste(c: int) -> float:
-            w = c * ctas / slots
-            return (math.ceil(w) - w) if w >= 1 else 0.0
-
-        best = min(range(max(2, n // 5), n // 2 + 1), key=lambda c: (round(waste(c) + waste(n - c), 3), c))
-        return best
+        return pipeline_split_point(n, max(plans[0].n_qubits, self.tile_bits), self.tile_bits, self._sm_count)
 
     def sample(self, plans: Sequence[PlanHandle], params: Sequence[Sequence[float]], shots: int, uniforms: np.ndarray) -> np.ndarray:
         if not plans:

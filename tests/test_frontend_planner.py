@@ -209,3 +209,39 @@ def test_planner_invariants():
     assert len(plan.sweeps) <= 2 * 6 + 2
     plan12 = sc.plan_circuit(gates.ops, 20, tile_bits=12)
     assert len(plan12.sweeps) <= len(plan.sweeps)
+
+
+def test_pipeline_split_point_fills_whole_waves():
+    """Host logic of the pipelined submission (engine.pipeline_split_point): 32 twenty-qubit evaluations on 148 SMs are cut
+    into 9 + 23 (1.95 and 4.97 waves of 592 resident sweep CTAs); small lists and large states are not split."""
+    from queasars_b200.engine import pipeline_split_point
+
+    assert pipeline_split_point(32, 20, 11, 148) == 9
+    assert pipeline_split_point(7, 20, 11, 148) is None
+    assert pipeline_split_point(32, 26, 11, 148) is None
+    for n in (8, 16, 24, 40, 64):
+        c = pipeline_split_point(n, 18, 11, 148)
+        assert n // 5 <= c <= n // 2 or c == 2
+
+
+def test_diagonal_energy_bitstring_evaluator_contract():
+    """DiagonalEnergyBitstringEvaluator keeps the BitstringEvaluator contract (bitstring_evaluation.py:7-61 of the reference:
+    length / charset validation, one float per string) and agrees with the oracle's diagonal energy; duplicate masks merge."""
+    import pickle
+
+    from queasars_b200 import BitstringEvaluatorException, DiagonalEnergyBitstringEvaluator
+
+    z, c = [1, 3, 8, 1, 5], [0.5, -1.0, 2.0, 0.25, 0.125]
+    ev = DiagonalEnergyBitstringEvaluator(4, z, c)
+    assert ev.input_length == 4
+    for state in range(16):
+        want = oq.diagonal_energy(state, list(zip(z, c)))
+        assert ev.evaluate_bitstring(format(state, "04b")) == pytest.approx(want, abs=1e-15)
+    np.testing.assert_allclose(ev.evaluate_states(np.arange(16, dtype=np.uint64)), [oq.diagonal_energy(s, list(zip(z, c))) for s in range(16)], atol=1e-15)
+    assert len(ev.diagonal_terms[0]) == 4  # the two terms on mask 1 were merged
+    with pytest.raises(BitstringEvaluatorException):
+        ev.evaluate_bitstring("01")
+    with pytest.raises(BitstringEvaluatorException):
+        ev.evaluate_bitstring("01a1")
+    clone = pickle.loads(pickle.dumps(ev))
+    assert clone.evaluate_bitstring("1010") == ev.evaluate_bitstring("1010")
