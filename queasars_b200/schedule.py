@@ -339,9 +339,12 @@ def plan_circuit(
             out.append(SweepPlan(tile_qubits, passes))
         return out
 
-    def count_sweeps(rng, p_accept: float) -> int:
+    def count_sweeps(rng, p_accept: float, limit: int) -> int:
+        """Sweeps this draw needs; gives up (returns ``limit``) as soon as it cannot end below ``limit``."""
         todo, n = list(remaining), 0
         while todo:
+            if n + 1 >= limit:
+                return limit
             _, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, MAX_SWEEP_OPS, rng, p_accept)
             if not chosen:
                 _, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, MAX_SWEEP_OPS)
@@ -360,7 +363,8 @@ def plan_circuit(
         best_n, best = len(sweeps), []  # draws that reach the smallest sweep count: (seed, p_accept)
         for trial in range(PLAN_TRIALS):
             p_accept = PLAN_ACCEPT[trial % len(PLAN_ACCEPT)]
-            n = count_sweeps(random.Random(seed0 + trial), p_accept)
+            # a draw is only interesting if it beats the best count, or ties it while full builds are still wanted
+            n = count_sweeps(random.Random(seed0 + trial), p_accept, best_n + 1 if len(best) < PLAN_FULL_BUILDS else best_n)
             if n < best_n:
                 best_n, best = n, []
             if n == best_n and len(best) < PLAN_FULL_BUILDS:
