@@ -192,8 +192,11 @@ def test_planner_invariants():
     seen = []
     for sw in plan.sweeps:
         assert len(sw.tile_qubits) == sc.TILE_BITS and sw.tile_qubits[:4] == [0, 1, 2, 3]
-        assert not any(b < 4 for b in sw.passes[0].reg_bits)
-        assert not any(b < 4 for b in sw.passes[-1].reg_bits)
+        if sc.ALLOW_LOW_EDGE_PASSES:  # no pass exists only to re-lay the tile out for the HBM access
+            assert all(ps.ops for ps in sw.passes) or len(sw.passes) == 1
+        else:  # first / last pass keep the low tile bits on the lanes (fully coalesced HBM accesses)
+            assert not any(b < 4 for b in sw.passes[0].reg_bits)
+            assert not any(b < 4 for b in sw.passes[-1].reg_bits)
         for ps in sw.passes:
             assert len(set(ps.reg_bits)) == 4
             seen += [po.op_index for po in ps.ops]
