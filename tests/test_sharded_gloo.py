@@ -159,3 +159,39 @@ def test_single_rank_no_swaps():
     sv.run(gl.from_circuit(build_circuit(instr, n)), values)
     assert sv.swaps_done == 0
     np.testing.assert_allclose(sv.gather_logical(), oq.statevector(instr, n, values), atol=1e-13)
+
+
+@pytest.mark.parametrize("n_local,lp", [(10, [9]), (11, [2, 10]), (12, [0, 5, 11]), (12, [3, 4, 5])])
+def test_fused_swap_work_order_is_the_bit_permutation(n_local, lp):
+    """NumPy mirror of swap_p2p_kernel's index arithmetic (queasars_b200/csrc/qb_kernels.cuh): element number t of rank r ->
+    destination rank d = run number XOR r, source index i with d's bits dropped in at the exchanged positions, destination index
+    i with those bits replaced by r's.  Over all ranks this must be exactly the permutation rank bit j <-> local bit lp[j], every
+    element moved once, and at any element number the ranks must target pairwise different peers."""
+    g, world, size = len(lp), 1 << len(lp), 1 << n_local
+    run_bits = min(10, n_local - g)
+    t = np.arange(size, dtype=np.int64)
+    lpmask = sum(1 << p for p in lp)
+    full_src = np.arange(world * size, dtype=np.int64)
+    landed = np.full(world * size, -1, dtype=np.int64)
+    dest_of_rank = []
+    for r in range(world):
+        d = ((t >> run_bits) & (world - 1)) ^ r
+        i = ((t >> (run_bits + g)) << run_bits) | (t & ((1 << run_bits) - 1))
+        for j, p in enumerate(lp):  # ascending: open a gap at p, drop in bit j of d
+            i = ((i >> p) << (p + 1)) | (i & ((1 << p) - 1)) | (((d >> j) & 1) << p)
+        assert np.array_equal(np.sort(i), t)  # every source element of the shard exactly once
+        rbits = sum(((r >> j) & 1) << p for j, p in enumerate(lp))
+        dst = (d << n_local) | (i & ~lpmask) | rbits
+        assert np.all(landed[dst] == -1)
+        landed[dst] = full_src[(r << n_local) | i]
+        dest_of_rank.append(d)
+    swapped = full_src.copy()
+    for j, p in enumerate(lp):
+        a, b = (full_src >> (n_local + j)) & 1, (full_src >> p) & 1
+        swapped &= ~((1 << (n_local + j)) | (1 << p))
+        swapped |= (b << (n_local + j)) | (a << p)
+    want = np.empty_like(full_src)
+    want[swapped] = full_src
+    assert np.array_equal(landed, want)
+    stacked = np.stack(dest_of_rank)  # ranks x element numbers
+    assert all(len(set(stacked[:, k])) == world for k in range(0, size, max(1, size // 64)))
