@@ -40,6 +40,7 @@ PASS_FLAG_WARP_LOCAL = 1  # qb_pass.flags bit 0
 ALLOW_LOW_EDGE_PASSES = os.environ.get("QB_ALLOW_LOW_EDGE", "1") != "0"
 PLAN_TRIALS = int(os.environ.get("QB_PLAN_TRIALS", "48"))  # randomised restarts of the sweep (tile) choice; 0 = greedy only
 PLAN_FULL_BUILDS = int(os.environ.get("QB_PLAN_FULL_BUILDS", "3"))  # how many of the best draws are planned in full (passes) before the winner is chosen
+PLAN_VISIT_BUDGET = 400_000  # op visits the restarts may spend per circuit (48 trials up to ~8 000 op-sweeps)
 PLAN_ACCEPT = (0.9, 0.8, 0.7)  # probability of accepting a new tile qubit in a randomised trial (cycled over the trials)
 PREFER_CONTROLS_ON_WARP_BITS = os.environ.get("QB_CTRL_WARP", "1") != "0"  # A/B switch, see DESIGN.md
 
@@ -361,7 +362,9 @@ def plan_circuit(
 
         seed0 = zlib.crc32(repr([(op.kind, op.target, op.control) for op in ops]).encode())
         best_n, best = len(sweeps), []  # draws that reach the smallest sweep count: (seed, p_accept)
-        for trial in range(PLAN_TRIALS):
+        # every trial walks the remaining ops once per sweep: cap the search for very long circuits (EVQE individuals are far below)
+        trials = min(PLAN_TRIALS, PLAN_VISIT_BUDGET // max(1, len(remaining) * len(sweeps)))
+        for trial in range(trials):
             p_accept = PLAN_ACCEPT[trial % len(PLAN_ACCEPT)]
             # a draw is only interesting if it beats the best count, or ties it while full builds are still wanted
             n = count_sweeps(random.Random(seed0 + trial), p_accept, best_n + 1 if len(best) < PLAN_FULL_BUILDS else best_n)
