@@ -105,6 +105,10 @@ int64_t qb_context_launch_count(qb_context* ctx);
 int qb_context_sm_count(qb_context* ctx);
 /* Upper bound for statevector workspace (bytes); 0 = 80 % of the device memory free at creation. */
 int qb_context_set_workspace_limit(qb_context* ctx, uint64_t bytes);
+/* Amplitude-index width of the sweep kernels: 32 = automatic (32-bit indices up to 31 local qubits, 64-bit above: the shards of
+ * BASELINE config C5), 64 = always the 64-bit-index kernels, so that the kernels a 35-qubit sharded state runs can be checked
+ * against the oracle at sizes the oracle finishes in seconds. */
+int qb_context_set_index_width(qb_context* ctx, int bits);
 int qb_context_synchronize(qb_context* ctx);
 
 /* --- plans: a parsed + scheduled circuit --------------------------------------------------------------

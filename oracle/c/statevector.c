@@ -69,3 +69,82 @@ void oracle_diag_table(double* table, int n, int n_terms, const uint64_t* z, con
         table[k] = e;
     }
 }
+
+/* Re sum_t (cr_t + i ci_t) <psi|P_t|psi> with P_t = i^{popcount(x_t & z_t)} X^{x_t} Z^{z_t}, i.e. P|k> = i^{nY} (-1)^{pc(k & z)} |k ^ x>
+ * ([upstream] Statevector.expectation_value -> expval_pauli_no_x / expval_pauli_with_x, ONE pass over the state per term, which
+ * is what the operator handed to /root/reference/queasars/circuit_evaluation/circuit_evaluation.py:200-215 costs on the CPU;
+ * the imaginary part is dropped at :215).  Same formula as oracle/qiskit_semantics.py:pauli_expectation. */
+double oracle_pauli_sum(const cplx* state, int n, int n_terms, const uint64_t* x, const uint64_t* z, const double* cr, const double* ci) {
+    const int64_t size = (int64_t)1 << n;
+    double total = 0.0;
+    for (int t = 0; t < n_terms; ++t) {
+        const uint64_t xm = x[t], zm = z[t];
+        double sr = 0.0, si = 0.0;
+        if (xm == 0) {
+#pragma omp parallel for schedule(static) reduction(+ : sr)
+            for (int64_t k = 0; k < size; ++k) {
+                const double p = state[k].re * state[k].re + state[k].im * state[k].im;
+                sr += (__builtin_popcountll((uint64_t)k & zm) & 1) ? -p : p;
+            }
+        } else {
+#pragma omp parallel for schedule(static) reduction(+ : sr, si)
+            for (int64_t k = 0; k < size; ++k) {
+                /* conj(psi[k ^ x]) * sign * psi[k] */
+                const cplx a = state[k], b = state[(uint64_t)k ^ xm];
+                const double s = (__builtin_popcountll((uint64_t)k & zm) & 1) ? -1.0 : 1.0;
+                sr += s * (b.re * a.re + b.im * a.im);
+                si += s * (b.re * a.im - b.im * a.re);
+            }
+        }
+        /* multiply by i^{nY} and by the coefficient, keep the real part */
+        const int ny = __builtin_popcountll(xm & zm) & 3;
+        double pr = sr, pi = si;
+        if (ny == 1) pr = -si, pi = sr;
+        else if (ny == 2) pr = -sr, pi = -si;
+        else if (ny == 3) pr = si, pi = -sr;
+        total += cr[t] * pr - (ci ? ci[t] : 0.0) * pi;
+    }
+    return total;
+}
+
+/* [upstream] Statevector.sample_memory -> numpy Generator.choice(p=probs): cdf = probs.cumsum() (sequential, left to right, like
+ * numpy's cumsum); cdf /= cdf[-1]; idx = cdf.searchsorted(uniforms, side='right')  (measure_quasi_distributions,
+ * /root/reference/queasars/circuit_evaluation/circuit_evaluation.py:29-59).  `cdf` is caller-provided scratch of 2^n doubles. */
+void oracle_sample(const cplx* state, int n, int shots, const double* uniforms, int64_t* out, double* cdf) {
+    const int64_t size = (int64_t)1 << n;
+    double run = 0.0;
+    for (int64_t k = 0; k < size; ++k) {
+        run += state[k].re * state[k].re + state[k].im * state[k].im;
+        cdf[k] = run;
+    }
+    const double last = cdf[size - 1];
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < size; ++k) cdf[k] /= last;
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < shots; ++s) {
+        const double u = uniforms[s];
+        int64_t lo = 0, hi = size; /* first index with cdf[i] > u */
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (cdf[mid] > u) hi = mid;
+            else lo = mid + 1;
+        }
+        out[s] = lo;
+    }
+}
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}

@@ -37,6 +37,12 @@ def load():
         lib.oracle_run_circuit.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.oracle_diag_table.restype = None
         lib.oracle_diag_table.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_pauli_sum.restype = ctypes.c_double
+        lib.oracle_pauli_sum.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_sample.restype = None
+        lib.oracle_sample.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_max_threads.restype = ctypes.c_int
+        lib.oracle_set_threads.argtypes = [ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -79,3 +85,35 @@ def diag_table(n, diag_terms):
     table = np.empty(1 << n, dtype=np.float64)
     lib.oracle_diag_table(table.ctypes.data, n, len(z), z.ctypes.data, c.ctypes.data)
     return table
+
+
+def pauli_sum(state, n, terms):
+    """Re sum_j c_j <psi|P_j|psi> for ``terms`` = [(label, coeff), ...] (labels little-endian like oq.pauli_label_to_masks): one
+    pass over the state per term, like the upstream estimator."""
+    lib = load()
+    masks = [oq.pauli_label_to_masks(label) for label, _ in terms]
+    x = np.asarray([m[0] for m in masks], dtype=np.uint64)
+    z = np.asarray([m[1] for m in masks], dtype=np.uint64)
+    cr = np.asarray([complex(c).real for _, c in terms], dtype=np.float64)
+    ci = np.asarray([complex(c).imag for _, c in terms], dtype=np.float64)
+    state = np.ascontiguousarray(state, dtype=np.complex128)
+    return float(lib.oracle_pauli_sum(state.ctypes.data, n, len(x), x.ctypes.data, z.ctypes.data, cr.ctypes.data, ci.ctypes.data))
+
+
+def sample_indices(state, n, uniforms):
+    """cumsum -> /= last -> searchsorted(side='right'), the chunk-free restatement of oq.sample_indices."""
+    lib = load()
+    state = np.ascontiguousarray(state, dtype=np.complex128)
+    uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(-1)
+    out = np.empty(uniforms.size, dtype=np.int64)
+    cdf = np.empty(1 << n, dtype=np.float64)
+    lib.oracle_sample(state.ctypes.data, n, uniforms.size, uniforms.ctypes.data, out.ctypes.data, cdf.ctypes.data)
+    return out
+
+
+def max_threads() -> int:
+    return int(load().oracle_max_threads())
+
+
+def set_threads(n: int) -> None:
+    load().oracle_set_threads(int(n))

@@ -37,6 +37,7 @@ def _declare(lib):
         "qb_context_launch_count": [c_void_p],
         "qb_context_set_workspace_limit": [c_void_p, c_uint64],
         "qb_context_synchronize": [c_void_p],
+        "qb_context_set_index_width": [c_void_p, c_int],
         "qb_plan_create": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, P(c_int64)],
         "qb_plan_destroy": [c_void_p, c_int64],
         "qb_plan_set_prefix": [c_void_p, c_int64, c_int64],
@@ -76,7 +77,7 @@ def _declare(lib):
 
 EXPORTED_SYMBOLS = (
     "qb_context_create qb_context_destroy qb_last_error qb_context_stream qb_context_launch_count "
-    "qb_context_set_workspace_limit qb_context_synchronize qb_plan_create qb_plan_destroy qb_plan_set_prefix qb_hamiltonian_create "
+    "qb_context_set_workspace_limit qb_context_synchronize qb_context_set_index_width qb_plan_create qb_plan_destroy qb_plan_set_prefix qb_hamiltonian_create "
     "qb_hamiltonian_destroy qb_hamiltonian_diag_energies qb_evaluate_expectation qb_sample qb_statevector "
     "qb_evaluate_expectation_submit qb_evaluate_expectation_collect qb_context_sm_count "
     "qb_batch_create qb_batch_set_params qb_batch_run qb_batch_run_timed qb_batch_read qb_batch_destroy qb_batch_stats "

@@ -153,6 +153,7 @@ struct qb_context {
     uint64_t default_workspace = uint64_t(8) << 30;  // 80 % of the memory free at creation (cudaMemGetInfo is slow: ask once)
     int64_t launches = 0;
     int64_t next_id = 1;
+    bool force_idx64 = false;  // qb_context_set_index_width(64): run the 64-bit-index sweep kernels at any size (tests)
     int tiles_log2 = -1;  // tiles per sweep CTA (log2); -1 = by size (4 tiles, 8 from 2^13 tiles per state on); QB_TILES_LOG2 overrides
     std::mutex mu;
     std::map<int64_t, std::unique_ptr<Plan>> plans;
@@ -375,7 +376,7 @@ int launch_circuits(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     // amplitude indices fit 32 bits up to 31 local qubits: cheaper address arithmetic for the common sizes
 #define QB_DISPATCH(R_, K_)                                                                                        \
     if (b.reg_bits == R_ && b.tile_bits == K_) {                                                                   \
-        if (b.n_eff <= 31)                                                                                         \
+        if (b.n_eff <= 31 && !ctx->force_idx64)                                                                    \
             return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_, uint32_t>(ctx, b, events)                  \
                                       : launch_sweeps_t<float, R_, K_, uint32_t>(ctx, b, events);                  \
         return b.dtype == QB_C128 ? launch_sweeps_t<double, R_, K_, uint64_t>(ctx, b, events)                      \
@@ -607,6 +608,14 @@ int64_t qb_context_launch_count(qb_context* ctx) { return ctx ? ctx->launches : 
 int qb_context_set_workspace_limit(qb_context* ctx, uint64_t bytes) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     ctx->workspace_limit = bytes;
+    return QB_OK;
+}
+
+int qb_context_set_index_width(qb_context* ctx, int bits) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    if (bits != 32 && bits != 64) return fail(QB_ERR_INVALID, "index width must be 32 (automatic) or 64");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->force_idx64 = bits == 64;
     return QB_OK;
 }
 

@@ -126,6 +126,10 @@ class Engine:
     def synchronize(self):
         _native.check(self._lib.qb_context_synchronize(self._ctx))
 
+    def set_index_width(self, bits: int):
+        """64: run the 64-bit-index sweep kernels (what > 31 local qubits use) at any size; 32: automatic."""
+        _native.check(self._lib.qb_context_set_index_width(self._ctx, int(bits)))
+
     # ------------------------------------------------------------------ compilation
     def compile_with_prefix_reuse(self, gates: GateList, dtype=None, min_prefix_ops: int = 4) -> PlanHandle:
         """Like ``compile``, but a leading run of parameter-free ops (the numerically bound layers of a partially

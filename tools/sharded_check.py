@@ -80,6 +80,10 @@ for q in range(args.n):
     lab[args.n - 1 - q] = "X"
     tfim_terms.append(("".join(lab), -0.5))
 tfim = SparsePauliOp.from_list(tfim_terms)
+# closed form on the product state prod_q RY(theta_q)|0>: <Z_q Z_q+1> = cos(theta_q) cos(theta_q+1), <X_q> = sin(theta_q)
+tfim_analytic = None
+if args.analytic:
+    tfim_analytic = float(-np.sum(np.cos(thetas[:-1]) * np.cos(thetas[1:])) - 0.5 * np.sum(np.sin(thetas)))
 swaps_before = sv.swaps_done
 torch.cuda.synchronize()
 t0 = time.perf_counter()
@@ -109,6 +113,7 @@ if rank == 0:
     out = {"n": args.n, "world": world, "n_local": sv.n_local, "gates": len(gates.ops), "swaps": swaps_in_run, "value": value, "analytic_value": analytic_value,
            "analytic_rel_err": None if analytic_value is None else abs(value - analytic_value) / max(1.0, abs(analytic_value)),
            "norm_err": abs(norm - 1.0), "run_s": t_run, "expectation_s": t_exp, "tfim_value": tfim_value, "tfim_s": t_tfim, "tfim_swaps": tfim_swaps,
+           "tfim_analytic_value": tfim_analytic, "tfim_analytic_rel_err": None if tfim_analytic is None else abs(tfim_value - tfim_analytic) / max(1.0, abs(tfim_analytic)),
            "sample_10k_s": t_sample, "sampled_energy_2000": sampled_energy, "swap_path": "p2p kernel (peer memory)" if sv._peer_ptrs is not None else "nccl all_to_all"}
     if swap_ms is not None:
         shard_bytes = 16 * (1 << sv.n_local)
