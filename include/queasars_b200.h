@@ -94,6 +94,7 @@ typedef struct qb_context qb_context;
 /* --- context ---------------------------------------------------------------------------------------- */
 /* One engine per (process, device).  `stream` = an existing cudaStream_t to launch on (e.g. torch's), or
  * NULL to let the context create its own non-blocking stream. */
+int qb_device_count(int* out); /* CUDA devices visible to the process (device sets of the multi-GPU primitives) */
 int qb_context_create(int device, void* stream, qb_context** out);
 int qb_context_destroy(qb_context* ctx);
 const char* qb_last_error(void);

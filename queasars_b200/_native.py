@@ -13,6 +13,7 @@ from ._build import LIB_PATH
 
 QB_OK = 0
 QB_C128, QB_C64 = 0, 1
+QB_ERR_INVALID, QB_ERR_CUDA, QB_ERR_MEMORY, QB_ERR_NOT_FOUND = -1, -2, -3, -4
 
 
 class NativeLibraryError(RuntimeError):
@@ -32,6 +33,7 @@ def _declare(lib):
     P = POINTER
     sigs = {
         "qb_context_create": [c_int, c_void_p, P(c_void_p)],
+        "qb_device_count": [P(c_int)],
         "qb_context_destroy": [c_void_p],
         "qb_context_stream": [c_void_p],
         "qb_context_launch_count": [c_void_p],
@@ -76,7 +78,7 @@ def _declare(lib):
 
 
 EXPORTED_SYMBOLS = (
-    "qb_context_create qb_context_destroy qb_last_error qb_context_stream qb_context_launch_count "
+    "qb_device_count qb_context_create qb_context_destroy qb_last_error qb_context_stream qb_context_launch_count "
     "qb_context_set_workspace_limit qb_context_synchronize qb_context_set_index_width qb_plan_create qb_plan_destroy qb_plan_set_prefix qb_hamiltonian_create "
     "qb_hamiltonian_destroy qb_hamiltonian_diag_energies qb_evaluate_expectation qb_sample qb_statevector "
     "qb_evaluate_expectation_submit qb_evaluate_expectation_collect qb_context_sm_count "
@@ -114,3 +116,9 @@ def check(code: int):
 
 def ptr(arr: np.ndarray):
     return arr.ctypes.data_as(c_void_p)
+
+
+def device_count() -> int:
+    out = c_int()
+    check(load().qb_device_count(ctypes.byref(out)))
+    return int(out.value)

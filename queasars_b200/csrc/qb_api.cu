@@ -331,8 +331,8 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
     {   // entries go through the pinned staging buffer so the copy is truly asynchronous
         const size_t bytes = sizeof(qb::BatchEntry) * size_t(batch);
         QB_TRY(b.entries.reserve(bytes));
+        QB_CUDA(cudaEventSynchronize(ctx->pin_entries_done));  // before a possible re-allocation: a copy out of it may be queued
         QB_TRY(ctx->pin_entries.reserve(bytes));
-        QB_CUDA(cudaEventSynchronize(ctx->pin_entries_done));
         std::memcpy(ctx->pin_entries.p, b.h_entries.data(), bytes);
         QB_CUDA(cudaMemcpyAsync(b.entries.p, ctx->pin_entries.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
         QB_CUDA(cudaEventRecord(ctx->pin_entries_done, ctx->stream));
@@ -527,7 +527,7 @@ int batch_read(qb_context* ctx, DeviceBatch& b, double* out_values) {
 size_t max_batch_for(qb_context* ctx, const Plan* pl) {
     const size_t state_bytes = (size_t(1) << pl->n_eff) * amp_bytes(pl->dtype);
     const size_t limit = ctx->workspace_limit ? ctx->workspace_limit : ctx->default_workspace;
-    return std::max<size_t>(1, limit / state_bytes);
+    return std::min<size_t>(65535, std::max<size_t>(1, limit / state_bytes));  // 65535: grid.y of the batched launches
 }
 
 }  // namespace
@@ -542,6 +542,14 @@ void qb_record_sizes(int32_t out[4]) {
     out[1] = int32_t(sizeof(qb_pass));
     out[2] = int32_t(sizeof(qb_pass_op));
     out[3] = int32_t(sizeof(qb_op_angles));
+}
+
+int qb_device_count(int* out) {
+    if (!out) return fail(QB_ERR_INVALID, "out is null");
+    int count = 0;
+    QB_CUDA(cudaGetDeviceCount(&count));
+    *out = count;
+    return QB_OK;
 }
 
 int qb_context_create(int device, void* stream, qb_context** out) {

@@ -32,6 +32,29 @@ def _dtype_code(dtype) -> int:
     return _DTYPES[key]
 
 
+# Host-side planning is device independent: one encoded program per (circuit structure, tile / register bits, start kind) serves
+# every engine of the process (multi-GPU primitives upload the same program to each device they use).
+_encoded_plans: dict = {}
+_encoded_lock = threading.Lock()
+
+
+def encoded_plan(gates: GateList, tile_bits: int, reg_bits: int, from_zero_state: bool):
+    """-> (n_sweeps, n_passes, n_pass_ops, (sweeps, passes, pass_ops, angles, init_ops)) of ``schedule.plan_circuit``."""
+    key = (int(tile_bits), int(reg_bits), bool(from_zero_state), gates.structure_key())
+    with _encoded_lock:
+        hit = _encoded_plans.get(key)
+    if hit is not None:
+        return hit
+    plan = schedule.plan_circuit(gates.ops, gates.n_qubits, tile_bits=tile_bits, reg_bits=reg_bits, product_prefix=from_zero_state)
+    arrays = schedule.encode_plan(plan, gates.ops)
+    hit = (len(arrays[0]), len(arrays[1]), sum(s.n_ops for s in plan.sweeps), arrays)
+    with _encoded_lock:
+        if len(_encoded_plans) > 4096:
+            _encoded_plans.clear()
+        _encoded_plans[key] = hit
+    return hit
+
+
 class PlanHandle:
     __slots__ = ("plan_id", "n_qubits", "n_params", "n_ops", "n_sweeps", "n_passes", "dtype", "prefix", "__weakref__")
 
@@ -150,9 +173,13 @@ class Engine:
             if self._prefix_bytes + state_bytes > self._prefix_budget:
                 return self.compile(gates, dtype)
             self._prefix_bytes += state_bytes
-        prefix = self.compile(GateList(gates.n_qubits, list(gates.ops[:split]), 0, ()), dtype, from_zero_state=True)
-        suffix = self.compile(GateList(gates.n_qubits, list(gates.ops[split:]), gates.n_params, gates.param_names), dtype, from_zero_state=False, cache=False)
-        _native.check(self._lib.qb_plan_set_prefix(self._ctx, suffix.plan_id, prefix.plan_id))
+        try:
+            prefix = self.compile(GateList(gates.n_qubits, list(gates.ops[:split]), 0, ()), dtype, from_zero_state=True)
+            suffix = self.compile(GateList(gates.n_qubits, list(gates.ops[split:]), gates.n_params, gates.param_names), dtype, from_zero_state=False, cache=False)
+            _native.check(self._lib.qb_plan_set_prefix(self._ctx, suffix.plan_id, prefix.plan_id))
+        except BaseException:
+            self._release_prefix_bytes(state_bytes)  # nothing was cached: give the budget back
+            raise
         suffix.prefix = prefix
         weakref.finalize(suffix, self._release_prefix_bytes, state_bytes)
         return suffix
@@ -169,9 +196,7 @@ class Engine:
             hit = self._plan_cache.get(key) if cache else None
         if hit is not None:
             return hit
-        plan = schedule.plan_circuit(gates.ops, gates.n_qubits, tile_bits=self.tile_bits, reg_bits=self.reg_bits, product_prefix=from_zero_state)
-        sweeps, passes, pass_ops, angles, init_ops = schedule.encode_plan(plan, gates.ops)
-        n_pass_ops = sum(s.n_ops for s in plan.sweeps)
+        _, _, n_pass_ops, (sweeps, passes, pass_ops, angles, init_ops) = encoded_plan(gates, self.tile_bits, self.reg_bits, from_zero_state)
         plan_id = c_int64()
         _native.check(
             self._lib.qb_plan_create(
@@ -224,6 +249,15 @@ class Engine:
             raise ValueError(f"{len(plans)} circuits but {len(params)} parameter vectors")
         ids = np.fromiter((p.plan_id for p in plans), dtype=np.int64, count=len(plans))
         offsets = np.zeros(len(plans) + 1, dtype=np.int64)
+        if isinstance(params, np.ndarray) and params.ndim == 2 and params.dtype == np.float64:
+            # one block of equally long parameter vectors (batched optimizer evaluation): no per-row conversion
+            width = params.shape[1]
+            for i, pl in enumerate(plans):
+                if pl.n_params != width:
+                    raise ValueError(f"circuit {i} has {pl.n_params} parameters but {width} values were given")
+            offsets[1:] = np.arange(1, len(plans) + 1, dtype=np.int64) * width
+            flat = np.ascontiguousarray(params).reshape(-1)
+            return ids, (flat if flat.size else np.zeros(1, dtype=np.float64)), offsets
         chunks = []
         for i, (pl, vals) in enumerate(zip(plans, params)):
             arr = np.asarray(vals, dtype=np.float64).reshape(-1)
@@ -252,10 +286,19 @@ class Engine:
                 for lo, hi in ((0, split), (split, len(plans))):
                     ids, flat, offsets = self._pack(plans[lo:hi], params[lo:hi])
                     _native.check(self._lib.qb_evaluate_expectation_submit(self._ctx, hi - lo, _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), ham.ham_id))
-            except Exception:
+            except _native.QbError as exc:
                 self._lib.qb_evaluate_expectation_collect(self._ctx, 0, None)  # drain whatever was queued
+                if exc.code != _native.QB_ERR_MEMORY:
+                    raise
+                split = None  # a chunk does not fit the statevector workspace: the one-shot call chunks by memory itself
+            except Exception:
+                self._lib.qb_evaluate_expectation_collect(self._ctx, 0, None)
                 raise
-            _native.check(self._lib.qb_evaluate_expectation_collect(self._ctx, len(plans), _native.ptr(out)))
+            if split is not None:
+                _native.check(self._lib.qb_evaluate_expectation_collect(self._ctx, len(plans), _native.ptr(out)))
+                return out
+        ids, flat, offsets = self._pack(plans, params)
+        _native.check(self._lib.qb_evaluate_expectation(self._ctx, len(plans), _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), ham.ham_id, _native.ptr(out)))
         return out
 
     def _pipeline_split(self, plans: Sequence[PlanHandle], params) -> Optional[int]:

@@ -28,7 +28,7 @@ import numpy as np
 from . import expectation as ex
 from .containers import QuasiDistribution
 from .engine import operator_terms
-from .primitives import B200EstimatorV2, B200SamplerV2
+from .primitives import B200EstimatorV2, B200SamplerV2, _circuit_fingerprint
 
 
 class CircuitEvaluatorException(Exception):
@@ -94,13 +94,15 @@ class _WithInitialState:
         if self._initial_state_circuit is None:
             return circuits
         cache = self.__dict__.setdefault("_composed", {})
+        init_fp = _circuit_fingerprint(self._initial_state_circuit)
         out = []
         for circ in circuits:
             hit = cache.get(id(circ))
-            if hit is None or hit[0] is not circ:
+            fp = (_circuit_fingerprint(circ), init_fp)  # either circuit edited in place since: compose again
+            if hit is None or hit[0] is not circ or hit[2] != fp:
                 if len(cache) > 1024:
                     cache.clear()
-                hit = cache[id(circ)] = (circ, self._initial_state_circuit.compose(circ, inplace=False))
+                hit = cache[id(circ)] = (circ, self._initial_state_circuit.compose(circ, inplace=False), fp)
             out.append(hit[1])
         return out
 

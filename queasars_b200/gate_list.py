@@ -89,6 +89,20 @@ class KernelOp:
         )
 
 
+def dfma_per_amplitude(op: KernelOp) -> float:
+    """FP64 multiply-add-class instructions per amplitude the sweep kernel spends on ``op`` (roofline accounting in bench.py):
+    a dense 2x2 gate costs 16 per amplitude pair, 14 when its top-left entry is real (no global phase), 12 when the bottom-left
+    entry is real as well (phi == 0: the R_Y * D form of the phase-deferred front end); a diagonal 4 per amplitude it touches;
+    a controlled op touches half of the amplitudes."""
+    if op.kind == DIAG:
+        per = 4.0
+    else:
+        real00 = op.gamma.slot < 0 and op.gamma.const == 0.0
+        real10 = real00 and op.phi.slot < 0 and op.phi.const == 0.0 and not getattr(op, "phi2", None)
+        per = 6.0 if real10 else (7.0 if real00 else 8.0)
+    return per * (1.0 if op.control < 0 else 0.5)
+
+
 @dataclass
 class GateList:
     n_qubits: int

@@ -23,6 +23,7 @@ from typing import Iterable, Optional, Sequence
 
 import numpy as np
 
+from . import _native
 from . import containers as ct
 from .batching import CoalescingQueue
 from .engine import Engine, HamiltonianHandle, PlanHandle
@@ -42,70 +43,152 @@ def get_engine(device: int = 0, dtype: str = "complex128") -> Engine:
         return eng
 
 
-class _CircuitCache:
-    """circuit object -> compiled plan, keyed by identity (the optimizer loop re-submits the *same* circuit
-    object on every objective call: evqe/evolutionary_algorithm/mutation.py:63-75)."""
+def _circuit_fingerprint(circuit) -> tuple:
+    """Cheap guard against in-place edits of a circuit between two evaluations (Qiskit circuits are mutable; the reference
+    re-transpiles on every call: transpiling_primitives.py:47, 73-80): instruction count and parameter count.  A circuit
+    whose fingerprint changed is re-parsed and re-compiled."""
+    try:
+        return (len(circuit.data), int(circuit.num_parameters) if hasattr(circuit, "num_parameters") else len(circuit.parameters))
+    except Exception:
+        return ()
 
-    def __init__(self, engine: Engine):
-        self._engine = engine
+
+def _operator_fingerprint(operator) -> tuple:
+    """Term count + hash of the coefficients (``SparsePauliOp.coeffs`` can be assigned in place)."""
+    try:
+        coeffs = np.asarray(operator.coeffs if hasattr(operator, "coeffs") else operator.masks()[2])
+        return (int(coeffs.size), hash(coeffs.tobytes()))
+    except Exception:
+        return ()
+
+
+class _CircuitCache:
+    """circuit object -> parsed gate list and, per device, compiled plan; keyed by identity (the optimizer loop re-submits the
+    *same* circuit object on every objective call: evqe/evolutionary_algorithm/mutation.py:63-75) and guarded by a
+    fingerprint so a circuit edited in place is compiled again."""
+
+    def __init__(self, engines: Sequence[Engine]):
+        self._engines = list(engines)
         self._lock = threading.Lock()
         self._by_id: dict = {}
 
-    def plan_for(self, circuit) -> Optional[PlanHandle]:
+    def _entry(self, circuit):
         key = id(circuit)
+        fp = _circuit_fingerprint(circuit)
         with self._lock:
             hit = self._by_id.get(key)
-            if hit is not None and hit[0]() is circuit:
-                return hit[1]
-        gates = from_circuit_or_none(circuit)
-        # identity-cached circuits are the ones an optimizer loop re-submits: worth caching their constant prefix state
-        plan = None if gates is None else self._engine.compile_with_prefix_reuse(gates)
+            if hit is not None and hit["ref"]() is circuit and hit["fp"] == fp:
+                return hit
+        entry = {"ref": None, "fp": fp, "gates": from_circuit_or_none(circuit), "plans": {}, "home": None}
         try:
-            ref = weakref.ref(circuit, lambda _r, k=key: self._by_id.pop(k, None))
+            entry["ref"] = weakref.ref(circuit, lambda _r, k=key: self._by_id.pop(k, None))
         except TypeError:  # not weak-referenceable: do not cache by identity
-            return plan
+            entry["ref"] = lambda: None
+            return entry
         with self._lock:
-            self._by_id[key] = (ref, plan)
+            self._by_id[key] = entry
+        return entry
+
+    def gates_for(self, circuit):
+        return self._entry(circuit)
+
+    def plan_for(self, circuit, slot: int = 0, entry=None) -> Optional[PlanHandle]:
+        entry = self._entry(circuit) if entry is None else entry
+        if entry["gates"] is None:
+            return None
+        plan = entry["plans"].get(slot)
+        if plan is None:
+            # identity-cached circuits are the ones an optimizer loop re-submits: worth caching their constant prefix state
+            plan = self._engines[slot].compile_with_prefix_reuse(entry["gates"])
+            entry["plans"][slot] = plan
         return plan
 
-    def bound_plan(self, circuit, values) -> PlanHandle:
+    def bound_plan(self, circuit, values, slot: int = 0) -> PlanHandle:
         """Slow path for circuits whose angles are not affine in single parameters: bind on the host."""
         bound = circuit.assign_parameters(list(values)) if len(values) else circuit
-        return self._engine.compile(from_circuit(bound))
+        return self._engines[slot].compile(from_circuit(bound))
+
+
+def _rotate_for_process(devices: list) -> list:
+    """Device order for this process.  A primitive pickled into worker processes (the reference's dask route: evqe.py:38-44,
+    mutation.py:194-218) keeps its device SET but every process starts filling it at a different device, so single-circuit
+    calls from different workers do not all land on the first GPU."""
+    if len(devices) < 2:
+        return devices
+    import os
+
+    k = os.getpid() % len(devices)
+    return devices[k:] + devices[:k]
 
 
 class _B200Primitive:
-    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, coalesce: bool = True):
+    """Shared runtime of the two primitives.  ``devices``: the GPUs this primitive may use -- a list of CUDA device indices
+    or "all" (every device visible to the process); default: the single ``device``.  One native engine per device, one
+    worker thread per device; every submitted list is split over the devices by estimated cost (sweeps x state size),
+    plans and Hamiltonians are replicated lazily, results come back in submission order.  This is the reference's
+    population parallelism (ThreadPoolExecutor / dask workers around ONE primitive: evqe.py:232-236, selection.py:75-82)
+    mapped onto several GPUs behind the unchanged evaluator interface; the evaluations are independent, so there is no
+    collective."""
+
+    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, coalesce: bool = True, devices=None):
         self.device, self.dtype, self.seed, self.coalesce = int(device), str(np.dtype(dtype).name), seed, bool(coalesce)
+        if devices is not None and devices != "all":
+            devices = [int(d) for d in devices]
+            if not devices or len(set(devices)) != len(devices):
+                raise ValueError("devices must be a non-empty list of distinct CUDA device indices, or 'all'")
+        self.devices = devices
+        self._origin_pid = None
         self._init_runtime()
 
     def _init_runtime(self):
-        self._engine_obj: Optional[Engine] = None
+        self._engines_obj: Optional[list] = None
         self._cache_obj: Optional[_CircuitCache] = None
         self._ham_cache: dict = {}
         self._queue_obj: Optional[CoalescingQueue] = None
+        self._pool_obj = None
         self._lock = threading.Lock()
+        self._rr = 0  # round-robin start of the device choice for small submissions
 
     # picklable: CUDA handles are per process and re-created lazily (the dask route of the reference pickles
     # evaluators + primitives into worker processes: evqe.py:38-44)
     def __getstate__(self):
-        return {"device": self.device, "dtype": self.dtype, "seed": self.seed, "coalesce": self.coalesce}
+        import os
+
+        return {"device": self.device, "dtype": self.dtype, "seed": self.seed, "coalesce": self.coalesce, "devices": self.devices,
+                "_origin_pid": self._origin_pid or os.getpid()}
 
     def __setstate__(self, state):
         self.__dict__.update(state)
         self._init_runtime()
 
+    def _device_list(self) -> list:
+        import os
+
+        if self.devices is None:
+            return [self.device]
+        devices = list(range(_native.device_count())) if self.devices == "all" else list(self.devices)
+        if not devices:
+            raise RuntimeError("no CUDA device visible (queasars_b200 has no CPU fallback)")
+        # un-pickled in another process than the one that configured it: start at a process-specific device
+        return _rotate_for_process(devices) if self._origin_pid not in (None, os.getpid()) else devices
+
+    @property
+    def engines(self) -> list:
+        with self._lock:
+            if self._engines_obj is None:
+                self._engines_obj = [get_engine(d, self.dtype) for d in self._device_list()]
+            return self._engines_obj
+
     @property
     def engine(self) -> Engine:
-        if self._engine_obj is None:
-            self._engine_obj = get_engine(self.device, self.dtype)
-        return self._engine_obj
+        return self.engines[0]
 
     @property
     def _cache(self) -> _CircuitCache:
+        engines = self.engines
         with self._lock:
             if self._cache_obj is None:
-                self._cache_obj = _CircuitCache(self.engine)
+                self._cache_obj = _CircuitCache(engines)
             return self._cache_obj
 
     @property
@@ -115,27 +198,124 @@ class _B200Primitive:
                 self._queue_obj = CoalescingQueue(self._execute)
             return self._queue_obj
 
-    def hamiltonian_for(self, operator, build_table=None) -> HamiltonianHandle:
-        key = (id(operator), build_table)
+    @property
+    def _pool(self):
+        from concurrent.futures import ThreadPoolExecutor
+
+        engines = self.engines
+        with self._lock:
+            if self._pool_obj is None:
+                self._pool_obj = ThreadPoolExecutor(max_workers=len(engines), thread_name_prefix="qb-device")
+            return self._pool_obj
+
+    def hamiltonian_for(self, operator, build_table=None, slot: int = 0) -> HamiltonianHandle:
+        key = (id(operator), build_table, slot)
+        fp = _operator_fingerprint(operator)
         with self._lock:
             hit = self._ham_cache.get(key)
-            if hit is not None and hit[0] is operator:
+            if hit is not None and hit[0] is operator and hit[2] == fp:
                 return hit[1]
-        handle = self.engine.hamiltonian(operator, build_table=build_table)
+        handle = self.engines[slot].hamiltonian(operator, build_table=build_table)
         with self._lock:
-            if len(self._ham_cache) > 64:
+            if len(self._ham_cache) > 64 * len(self.engines):
                 self._ham_cache.clear()
-            self._ham_cache[key] = (operator, handle)
+            self._ham_cache[key] = (operator, handle, fp)
         return handle
 
-    def _resolve(self, circuit, values) -> tuple[PlanHandle, Sequence[float]]:
-        """(plan, parameter values as handed in): the float64 conversion happens chunk by chunk inside the engine's
-        pipelined submission, overlapped with the GPU work of the previous chunk."""
-        plan = self._cache.plan_for(circuit)
-        if plan is None:
-            values = np.asarray(values if values is not None else (), dtype=np.float64).reshape(-1)
-            return self._cache.bound_plan(circuit, values), np.zeros(0)
-        return plan, (values if values is not None else ())
+    # ------------------------------------------------------------------ splitting a submission over the devices
+    def _assign(self, entries: Sequence, costs: Sequence[float]) -> list:
+        """entries[i] = cache entry of circuit i (or None) -> device slot per entry.  Greedy longest-processing-time over
+        circuits (all rows of one circuit object stay together unless that circuit alone is more than a device's share,
+        then its rows are dealt out), preferring the device that already holds the circuit's plan / cached prefix state
+        while that does not unbalance the split."""
+        n_dev = len(self.engines)
+        if n_dev == 1:
+            return [0] * len(entries)
+        groups: dict = {}
+        for i, en in enumerate(entries):
+            groups.setdefault(id(en) if en is not None else ("row", i), []).append(i)
+        total = float(sum(costs)) or 1.0
+        share = total / n_dev
+        units = []  # (cost, rows, home)
+        for rows in groups.values():
+            en = entries[rows[0]]
+            home = en["home"] if en is not None else None
+            cost = sum(costs[i] for i in rows)
+            if cost > 1.25 * share and len(rows) > 1:  # one circuit, many parameter vectors: deal the rows out
+                per = max(1, int(len(rows) * share / cost))
+                for lo in range(0, len(rows), per):
+                    part = rows[lo : lo + per]
+                    units.append((sum(costs[i] for i in part), part, None))
+            else:
+                units.append((cost, rows, home))
+        units.sort(key=lambda u: -u[0])
+        load = [0.0] * n_dev
+        out = [0] * len(entries)
+        with self._lock:
+            start = self._rr
+            self._rr = (self._rr + 1) % n_dev
+        for cost, rows, home in units:
+            best = min(range(n_dev), key=lambda d: (load[d], (d - start) % n_dev))
+            if home is not None and load[home] <= load[best] + 0.5 * cost:
+                best = home
+            load[best] += cost
+            for i in rows:
+                out[i] = best
+                if entries[i] is not None and entries[i]["home"] is None:
+                    entries[i]["home"] = best
+        return out
+
+    def _resolve_all(self, circuits, parameter_values):
+        """-> list of (slot, plan, values) in submission order."""
+        cache = self._cache
+        entries = [cache.gates_for(c) for c in circuits]
+        costs = []
+        for en in entries:
+            gates = en["gates"]
+            costs.append(float(max(1, len(gates.ops))) if gates is not None else 1.0)
+        slots = self._assign(entries, costs)
+        out = []
+        for circuit, values, en, slot in zip(circuits, parameter_values, entries, slots):
+            plan = cache.plan_for(circuit, slot, en)
+            if plan is None:
+                values = np.asarray(values if values is not None else (), dtype=np.float64).reshape(-1)
+                out.append((slot, cache.bound_plan(circuit, values, slot), np.zeros(0)))
+            else:
+                # the float64 conversion happens chunk by chunk inside the engine's pipelined submission, overlapped with
+                # the GPU work of the previous chunk
+                out.append((slot, plan, values if values is not None else ()))
+        return out
+
+    def _run_per_device(self, resolved, call):
+        """Group ``resolved`` = [(slot, plan, values)] by device, run ``call(slot, plans, params)`` on every device's own
+        worker thread, return the per-entry results in submission order."""
+        by_slot: dict = {}
+        for i, (slot, _, _) in enumerate(resolved):
+            by_slot.setdefault(slot, []).append(i)
+        results = [None] * len(resolved)
+
+        def work(slot, rows):
+            return call(slot, [resolved[i][1] for i in rows], [resolved[i][2] for i in rows])
+
+        if len(by_slot) == 1:
+            ((slot, rows),) = by_slot.items()
+            for i, r in zip(rows, work(slot, rows)):
+                results[i] = r
+            return results
+        futures = {slot: self._pool.submit(work, slot, rows) for slot, rows in by_slot.items()}
+        error = None
+        for slot, fut in futures.items():
+            try:
+                for i, r in zip(by_slot[slot], fut.result()):
+                    results[i] = r
+            except BaseException as exc:  # wait for every device before surfacing the first failure
+                error = error or exc
+        if error is not None:
+            raise error
+        return results
+
+    def devices_used(self) -> list:
+        return [e.device for e in self.engines]
 
     def _submit(self, key, payload):
         if self.coalesce:
@@ -161,8 +341,8 @@ def _param_rows(values) -> tuple[np.ndarray, tuple]:
 class B200EstimatorV2(_B200Primitive):
     """EstimatorV2-contract primitive backed by the CUDA statevector engine."""
 
-    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, default_precision: float = 0.0, coalesce: bool = True):
-        super().__init__(device, dtype, seed, coalesce)
+    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, default_precision: float = 0.0, coalesce: bool = True, devices=None):
+        super().__init__(device, dtype, seed, coalesce, devices)
         self.default_precision = default_precision
 
     def __getstate__(self):
@@ -170,22 +350,28 @@ class B200EstimatorV2(_B200Primitive):
 
     def expectation_values(self, circuits, parameter_values, operator) -> np.ndarray:
         """Fast path used by ``B200OperatorCircuitEvaluator``: exact <H> of (circuit_i, params_i)."""
-        ham = self.hamiltonian_for(operator)
-        resolved = [self._resolve(c, v) for c, v in zip(circuits, parameter_values)]
-        return np.asarray(self._submit(("exp", ham.ham_id), (ham, resolved)))
+        circuits, parameter_values = list(circuits), list(parameter_values)
+        if len(circuits) != len(parameter_values):
+            raise ValueError(f"{len(circuits)} circuits but {len(parameter_values)} parameter vectors")
+        if not circuits:
+            return np.zeros(0)
+        self.hamiltonian_for(operator)  # validates the operator (and builds its device form) before anything is queued
+        return np.asarray(self._submit(("exp", id(operator), _operator_fingerprint(operator)), (operator, circuits, parameter_values)))
 
     def _execute(self, key, payloads):
-        ham = payloads[0][0]
-        plans, params, sizes = [], [], []
-        for _, resolved in payloads:
-            sizes.append(len(resolved))
-            for plan, vals in resolved:
-                plans.append(plan)
-                params.append(vals)
-        flat = self.engine.expectation(plans, params, ham)
+        operator = payloads[0][0]
+        circuits, values, sizes = [], [], []
+        for _, circs, vals in payloads:
+            sizes.append(len(circs))
+            circuits.extend(circs)
+            values.extend(vals)
+        resolved = self._resolve_all(circuits, values)
+        flat = self._run_per_device(
+            resolved, lambda slot, plans, params: self.engines[slot].expectation(plans, params, self.hamiltonian_for(operator, slot=slot))
+        )
         out, pos = [], 0
         for n in sizes:
-            out.append(flat[pos : pos + n])
+            out.append(np.asarray(flat[pos : pos + n], dtype=np.float64))
             pos += n
         return out
 
@@ -229,11 +415,22 @@ def _single_observable(observables):
     return obs
 
 
+def _check_measure_all(circuit) -> None:
+    """The sampler returns ONE full-width register named "meas" -- what ``measure_all`` produces and the only shape QUEASARS
+    consumes (circuit_evaluation.py:50-55).  Circuits with other classical registers would get a silently different result
+    from upstream's per-register BitArrays, so they are rejected."""
+    cregs = getattr(circuit, "cregs", None)
+    if not cregs:
+        return
+    if len(cregs) != 1 or getattr(cregs[0], "name", "meas") != "meas" or len(cregs[0]) != int(circuit.num_qubits):
+        raise NotImplementedError("B200SamplerV2 supports circuits measured with measure_all() only (one register 'meas' over all qubits)")
+
+
 class B200SamplerV2(_B200Primitive):
     """SamplerV2-contract primitive: shots drawn on the GPU from the exact statevector distribution."""
 
-    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, default_shots: int = 1024, coalesce: bool = True):
-        super().__init__(device, dtype, seed, coalesce)
+    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, default_shots: int = 1024, coalesce: bool = True, devices=None):
+        super().__init__(device, dtype, seed, coalesce, devices)
         self.default_shots = default_shots
 
     def __getstate__(self):
@@ -241,26 +438,40 @@ class B200SamplerV2(_B200Primitive):
 
     def sample_indices(self, circuits, parameter_values, shots: int) -> np.ndarray:
         """Fast path used by the B200 sampler evaluators: int64 array [len(circuits), shots] of basis states."""
-        resolved = [self._resolve(c, v) for c, v in zip(circuits, parameter_values)]
-        return np.asarray(self._submit(("smp", int(shots)), resolved))
+        circuits, parameter_values = list(circuits), list(parameter_values)
+        if len(circuits) != len(parameter_values):
+            raise ValueError(f"{len(circuits)} circuits but {len(parameter_values)} parameter vectors")
+        if not circuits:
+            return np.zeros((0, int(shots)), dtype=np.int64)
+        # circuits of different widths must not be merged into one native batch: the width is part of the coalescing key
+        widths = {int(c.num_qubits) for c in circuits}
+        if len(widths) != 1:
+            raise ValueError("all circuits of one sampler submission must act on the same number of qubits")
+        return np.asarray(self._submit(("smp", int(shots), widths.pop()), (circuits, parameter_values)))
 
     def _execute(self, key, payloads):
         shots = key[1]
-        plans, params, sizes = [], [], []
-        for resolved in payloads:
-            sizes.append(len(resolved))
-            for plan, vals in resolved:
-                plans.append(plan)
-                params.append(vals)
-        # a fresh default_rng(seed) per pub when seed is an int (or None); a shared Generator is consumed in order
+        circuits, values, sizes = [], [], []
+        for circs, vals in payloads:
+            sizes.append(len(circs))
+            circuits.extend(circs)
+            values.extend(vals)
+        resolved = self._resolve_all(circuits, values)
+        # a fresh default_rng(seed) per pub when seed is an int (or None); a shared Generator is consumed in submission order
         if isinstance(self.seed, np.random.Generator):
-            uniforms = np.stack([self.seed.random(shots) for _ in plans]) if plans else np.zeros((0, shots))
+            uniforms = np.stack([self.seed.random(shots) for _ in resolved])
         else:
-            uniforms = np.stack([np.random.default_rng(self.seed).random(shots) for _ in plans]) if plans else np.zeros((0, shots))
-        flat = self.engine.sample(plans, params, shots, uniforms)
+            one = np.random.default_rng(self.seed).random(shots) if self.seed is not None else None
+            uniforms = np.stack([one if one is not None else np.random.default_rng().random(shots) for _ in resolved])
+        rows_of: dict = {}
+        for i, (slot, _, _) in enumerate(resolved):
+            rows_of.setdefault(slot, []).append(i)
+        flat = self._run_per_device(
+            resolved, lambda slot, plans, params: list(self.engines[slot].sample(plans, params, shots, uniforms[rows_of[slot]]))
+        )
         out, pos = [], 0
         for n in sizes:
-            out.append(flat[pos : pos + n])
+            out.append(np.stack(flat[pos : pos + n]))
             pos += n
         return out
 
@@ -273,6 +484,7 @@ class B200SamplerV2(_B200Primitive):
                 rows, shape = _param_rows(pub.parameter_values)
                 if shape != ():
                     raise NotImplementedError("B200SamplerV2 supports one parameter vector per pub")
+                _check_measure_all(pub.circuit)
                 idx = self.sample_indices([pub.circuit], [rows[0]], n_shots)[0]
                 reg = ct.ShotRegister(idx, int(pub.circuit.num_qubits))
                 results.append(ct.SamplerPubResult(ct.DataBin(meas=reg, shape=()), metadata={"shots": n_shots, "circuit_metadata": {}}))
