@@ -309,7 +309,7 @@ def run_b200(args):
     values = evaluator.evaluate_circuits(circuits, params)  # compiles plans, builds the table
     assert len(values) == POPULATION and all(np.isfinite(values))
 
-    plans = [estimator._cache.plan_for(c) for c in circuits]
+    plans = [estimator._cache.plan_for(c, probabilities_only=True) for c in circuits]  # the plans the evaluator call above compiled (diagonal H)
     ham = estimator.hamiltonian_for(operator)
     batch = engine.resident_batch(plans, ham)
     h2d = batch.set_params(params)
@@ -376,8 +376,10 @@ def run_b200(args):
     from queasars_b200 import schedule as _sc
 
     dfma = 0.0
+    from queasars_b200 import engine as _eng
+
     for c in circuits:
-        ops = estimator._cache.gates_for(c)["gates"].ops
+        ops = _eng.rewritten(estimator._cache.gates_for(c)["gates"], drop_final_phases=True).ops
         _, remaining = _sc.split_product_prefix(ops, N_QUBITS)
         dfma += sum(_gl.dfma_per_amplitude(ops[i]) for i in remaining) * float(1 << N_QUBITS)
     fp64_peak = 16.9e12

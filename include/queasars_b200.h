@@ -78,12 +78,15 @@ typedef struct qb_pass_op {
     uint8_t variant, ctrl_qubit, tgt_qubit;
 } qb_pass_op;
 
-/* angle sources of one op: value_j = cnst[j] + coeff[j] * params[slot[j]]  (slot < 0: constant);
- * j = 0..3 -> gamma, theta, phi, lam.  This is where the flat parameter vector of
- * circuit_evaluation.py:205-207 is bound ([upstream] EstimatorPub.coerce order = sorted parameter names). */
+/* angle sources of one op: value_j = cnst[j] + coeff[j] * params[slot[j]] + coeff2[j] * params[slot2[j]]  (slot < 0: no such
+ * term); j = 0..3 -> gamma, theta, phi, lam.  This is where the flat parameter vector of
+ * circuit_evaluation.py:205-207 is bound ([upstream] EstimatorPub.coerce order = sorted parameter names).  The second term
+ * carries the deferred trailing phase of the previous gate on the same qubit (queasars_b200/gate_list.py: defer_phases). */
 typedef struct qb_op_angles {
     int32_t slot[4];
+    int32_t slot2[4];
     double coeff[4];
+    double coeff2[4];
     double cnst[4];
     int32_t kind;
     int32_t pad;

@@ -711,7 +711,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     }
     for (int o = 0; o < n_ops; ++o)
         for (int j = 0; j < 4; ++j)
-            if (ops[o].slot[j] >= n_params) return fail(QB_ERR_INVALID, "angle slot out of range");
+            if (ops[o].slot[j] >= n_params || ops[o].slot2[j] >= n_params) return fail(QB_ERR_INVALID, "angle slot out of range");
     bool has_init = false;
     if (init_ops) {
         std::vector<char> used(size_t(std::max(n_ops, 1)), 0);

@@ -108,7 +108,9 @@ __device__ __forceinline__ double ld_table(const double* p) {
 // REAL00: the matrix's top-left entry is real (every gate without a global phase, e^{i gamma} = 1: all of EVQE's u / cu3) -- two of
 // the sixteen multiply-adds per pair vanish.  The flag is a property of the plan (gamma identically 0), so it is part of the
 // dispatch word; skipping the two FMAs is bit-identical to executing them with m00.y = +0.
-template <typename T, int R, int B, int CB, bool REAL00 = false>
+// REAL10: the bottom-left entry is real as well (phi == 0: the R_Y(theta) * D(lam) form every uncontrolled gate has after the
+// front end's phase deferral, gate_list.py: defer_phases) -- two more multiply-adds vanish, 12 per pair.
+template <typename T, int R, int B, int CB, bool REAL00 = false, bool REAL10 = false>
 __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type m00, const typename Cx<T>::type m01,
                                             const typename Cx<T>::type m10, const typename Cx<T>::type m11) {
     constexpr int kNReg = 1 << R;
@@ -126,8 +128,10 @@ __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], c
         T t3 = m10.x * x.y;
         t0 = fma(-m01.y, y.y, t0);
         t1 = fma(m01.y, y.x, t1);
-        t2 = fma(-m10.y, x.y, t2);
-        t3 = fma(m10.y, x.x, t3);
+        if (!REAL10) {
+            t2 = fma(-m10.y, x.y, t2);
+            t3 = fma(m10.y, x.x, t3);
+        }
         if (!REAL00) {
             t0 = fma(-m00.y, x.y, t0);
             t1 = fma(m00.y, x.x, t1);
@@ -174,6 +178,7 @@ constexpr int kMaxInitQubits = 64;
 
 // dispatch word: variant | cpos << 6 | dpos << 11 | dflag << 16 | cb << 17 | tb << 20 | treg << 23
 //   variant bit 5 (dense ops): the matrix's top-left entry is real (gamma == 0) -> 14 instead of 16 multiply-adds per pair
+//   variant 48 + b (uncontrolled dense on register bit b): the whole first column is real (gamma == phi == 0) -> 12
 //   cpos  tile-local position of a thread-bit control; 31 = none (bit 31 of the test word is always set), 30 = an external
 //         control that is 0 for this tile (bit 30 is never set)
 //   dpos  tile-local position of a thread-bit diagonal target; 31 = use dflag (external target, resolved per tile)
@@ -192,24 +197,24 @@ constexpr size_t sweep_smem_bytes() {
 }
 
 // apply_dense for a (B, CB) pair that may not exist for this R (keeps the case lists below uniform)
-template <typename T, int R, int B, int CB, bool REAL00>
+template <typename T, int R, int B, int CB, bool REAL00, bool REAL10 = false>
 __device__ __forceinline__ void dense_if(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
-    if constexpr (B < R && CB < R && B != CB) apply_dense<T, R, B, CB, REAL00>(a, m[0], m[1], m[2], m[3]);
+    if constexpr (B < R && CB < R && B != CB) apply_dense<T, R, B, CB, REAL00, REAL10>(a, m[0], m[1], m[2], m[3]);
 }
 
 // uncontrolled dense gate on register bit v (< R): two predictable branches
-template <typename T, int R, bool REAL00>
+template <typename T, int R, bool REAL00, bool REAL10 = false>
 __device__ __forceinline__ void dense_by_bit(uint32_t v, typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
     if (v & 2u) {
         if constexpr (R > 3) {
-            if (v & 1u) dense_if<T, R, 3, -1, REAL00>(a, m);
-            else dense_if<T, R, 2, -1, REAL00>(a, m);
+            if (v & 1u) dense_if<T, R, 3, -1, REAL00, REAL10>(a, m);
+            else dense_if<T, R, 2, -1, REAL00, REAL10>(a, m);
         } else {
-            dense_if<T, R, 2, -1, REAL00>(a, m);
+            dense_if<T, R, 2, -1, REAL00, REAL10>(a, m);
         }
     } else {
-        if (v & 1u) dense_if<T, R, 1, -1, REAL00>(a, m);
-        else dense_if<T, R, 0, -1, REAL00>(a, m);
+        if (v & 1u) dense_if<T, R, 1, -1, REAL00, REAL10>(a, m);
+        else dense_if<T, R, 0, -1, REAL00, REAL10>(a, m);
     }
 }
 
@@ -243,7 +248,12 @@ __device__ __forceinline__ void apply_op(uint32_t word, uint32_t e_thr, typename
         return sel ? m[3] : m[0];
     };
     // The common cases are reached by predictable branches instead of the jump table (+2 %), the commonest first: an
-    // uncontrolled dense gate with a real top-left entry (bit 5 of the variant) -- every `u` of an EVQE circuit.
+    // uncontrolled dense gate with a real first column (variants 48 + b: every `u` of an EVQE circuit after phase deferral),
+    // then one with a real top-left entry only (bit 5 of the variant).
+    if ((variant ^ 48u) < uint32_t(R)) {
+        dense_by_bit<T, R, true, true>(variant & 3u, a, m);
+        return;
+    }
     if ((variant ^ 32u) < uint32_t(R)) {
         dense_by_bit<T, R, true>(variant & 3u, a, m);
         return;
@@ -350,7 +360,11 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                     const int b = po.tgt_pos;
                     variant = rcb < 0 ? uint32_t(b) : uint32_t(R + b * (R - 1) + (rcb < b ? rcb : rcb - 1));
                     const qb_op_angles& ang = ge.angles[po.op_index];
-                    if (ang.slot[0] < 0 && ang.cnst[0] == 0.0) variant |= 32u;  // gamma == 0: m00 = cos(theta / 2) is real
+                    if (ang.slot[0] < 0 && ang.slot2[0] < 0 && ang.cnst[0] == 0.0) {
+                        variant |= 32u;  // gamma == 0: m00 = cos(theta / 2) is real
+                        // phi == 0 too: m10 = sin(theta / 2) is real (uncontrolled gates only have such bodies)
+                        if (rcb < 0 && ang.slot[2] < 0 && ang.slot2[2] < 0 && ang.cnst[2] == 0.0) variant |= 16u;
+                    }
                 } else {
                     if (po.tgt_kind == QB_K_THREAD) dpos = po.tgt_pos;
                     else if (po.tgt_kind == QB_K_EXT) extt = po.tgt_pos;
@@ -577,7 +591,10 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
 __device__ __forceinline__ void bind_matrix(const qb_op_angles& ang, const double* __restrict__ params, double* __restrict__ m) {
     double v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = ang.cnst[j] + (ang.slot[j] >= 0 ? ang.coeff[j] * params[ang.slot[j]] : 0.0);
+    for (int j = 0; j < 4; ++j) {
+        v[j] = ang.cnst[j] + (ang.slot[j] >= 0 ? ang.coeff[j] * params[ang.slot[j]] : 0.0);
+        if (ang.slot2[j] >= 0) v[j] += ang.coeff2[j] * params[ang.slot2[j]];
+    }
     const double g = v[0], t = v[1], p = v[2], l = v[3];
     double s, c;
     if (ang.kind == QB_OP_DIAG) {

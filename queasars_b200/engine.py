@@ -20,7 +20,17 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _native, schedule
-from .gate_list import GateList
+from .gate_list import GateList, defer_phases
+
+DEFER_PHASES = os.environ.get("QB_DEFER_PHASES", "1") != "0"  # A/B switch of the R_Y * D rewrite (gate_list.defer_phases)
+
+
+def rewritten(gates: GateList, drop_final_phases: bool = False) -> GateList:
+    """The gate list the engine really plans: trailing phases of uncontrolled gates deferred (12 instead of 14 multiply-adds
+    per amplitude pair), and dropped at the end of the circuit when the caller only needs |psi_k|^2."""
+    if not DEFER_PHASES:
+        return gates
+    return GateList(gates.n_qubits, defer_phases(gates.ops, drop_final_phases), gates.n_params, gates.param_names)
 
 _DTYPES = {"complex128": _native.QB_C128, "c128": _native.QB_C128, "complex64": _native.QB_C64, "c64": _native.QB_C64}
 
@@ -154,28 +164,29 @@ class Engine:
         _native.check(self._lib.qb_context_set_index_width(self._ctx, int(bits)))
 
     # ------------------------------------------------------------------ compilation
-    def compile_with_prefix_reuse(self, gates: GateList, dtype=None, min_prefix_ops: int = 4) -> PlanHandle:
+    def compile_with_prefix_reuse(self, gates: GateList, dtype=None, min_prefix_ops: int = 4, drop_final_phases: bool = False) -> PlanHandle:
         """Like ``compile``, but a leading run of parameter-free ops (the numerically bound layers of a partially
         parameterised EVQE circuit: evqe/evolutionary_algorithm/individual.py:288-322) is compiled as a separate plan
         whose resulting state is computed once and cached on the device; every evaluation then only applies the
         remaining ops.  The returned handle owns the cached state: it is not shared through
         the structural plan cache and is released with the handle.  Falls back to ``compile`` when there is nothing
         to reuse or the cached states would exceed a quarter of the workspace budget."""
+        gates = rewritten(gates, drop_final_phases)  # before the split: the pending phases cross the prefix / suffix boundary
         split = 0
         for op in gates.ops:
-            if any(a.slot >= 0 for a in op.angles):
+            if any(a.slot >= 0 or a.slot2 >= 0 for a in op.angles):
                 break
             split += 1
         state_bytes = (16 if (self._dtype_code if dtype is None else _dtype_code(dtype)) == _native.QB_C128 else 8) << max(gates.n_qubits, self.tile_bits)
         if split < min_prefix_ops or split == len(gates.ops) or gates.n_params == 0:
-            return self.compile(gates, dtype)
+            return self.compile(gates, dtype, defer=False)
         with self._lock:
             if self._prefix_bytes + state_bytes > self._prefix_budget:
-                return self.compile(gates, dtype)
+                return self.compile(gates, dtype, defer=False)
             self._prefix_bytes += state_bytes
         try:
-            prefix = self.compile(GateList(gates.n_qubits, list(gates.ops[:split]), 0, ()), dtype, from_zero_state=True)
-            suffix = self.compile(GateList(gates.n_qubits, list(gates.ops[split:]), gates.n_params, gates.param_names), dtype, from_zero_state=False, cache=False)
+            prefix = self.compile(GateList(gates.n_qubits, list(gates.ops[:split]), 0, ()), dtype, from_zero_state=True, defer=False)
+            suffix = self.compile(GateList(gates.n_qubits, list(gates.ops[split:]), gates.n_params, gates.param_names), dtype, from_zero_state=False, cache=False, defer=False)
             _native.check(self._lib.qb_plan_set_prefix(self._ctx, suffix.plan_id, prefix.plan_id))
         except BaseException:
             self._release_prefix_bytes(state_bytes)  # nothing was cached: give the budget back
@@ -188,9 +199,13 @@ class Engine:
         with self._lock:
             self._prefix_bytes -= nbytes
 
-    def compile(self, gates: GateList, dtype=None, from_zero_state: bool = True, cache: bool = True) -> PlanHandle:
-        """``from_zero_state=False``: the plan will be applied to an existing state (no product-state prefix)."""
+    def compile(self, gates: GateList, dtype=None, from_zero_state: bool = True, cache: bool = True, defer: bool = True, drop_final_phases: bool = False) -> PlanHandle:
+        """``from_zero_state=False``: the plan will be applied to an existing state (no product-state prefix).
+        ``drop_final_phases=True``: the caller only needs |psi_k|^2 of the result (diagonal observable, sampling): the
+        diagonal phases left pending at the end of the circuit are not applied (``rewritten``)."""
         code = self._dtype_code if dtype is None else _dtype_code(dtype)
+        if defer:
+            gates = rewritten(gates, drop_final_phases)
         key = (code, bool(from_zero_state), gates.structure_key())
         with self._lock:
             hit = self._plan_cache.get(key) if cache else None

@@ -34,20 +34,41 @@ class UnsupportedCircuitError(ValueError):
 
 @dataclass(frozen=True)
 class Angle:
-    """value = const + coeff * params[slot]   (slot == -1: constant)."""
+    """value = const + coeff * params[slot] + coeff2 * params[slot2]   (slot == -1: no such term).  Circuits hand in angles
+    with one parameter; the second term appears when the phase-deferral rewrite (``defer_phases``) adds the trailing phase of
+    the previous gate on a qubit to the next gate's angles."""
 
     slot: int = -1
     coeff: float = 0.0
     const: float = 0.0
+    slot2: int = -1
+    coeff2: float = 0.0
 
     def scaled(self, s: float) -> "Angle":
-        return Angle(self.slot, self.coeff * s, self.const * s)
+        return Angle(self.slot, self.coeff * s, self.const * s, self.slot2, self.coeff2 * s)
 
     def shifted(self, c: float) -> "Angle":
-        return Angle(self.slot, self.coeff, self.const + c)
+        return Angle(self.slot, self.coeff, self.const + c, self.slot2, self.coeff2)
 
     def value(self, params: Sequence[float]) -> float:
-        return self.const + (self.coeff * params[self.slot] if self.slot >= 0 else 0.0)
+        v = self.const + (self.coeff * params[self.slot] if self.slot >= 0 else 0.0)
+        return v + (self.coeff2 * params[self.slot2] if self.slot2 >= 0 else 0.0)
+
+    @property
+    def is_zero(self) -> bool:
+        return self.slot < 0 and self.slot2 < 0 and self.const == 0.0
+
+    def plus(self, other: "Angle", sign: float = 1.0) -> Optional["Angle"]:
+        """self + sign * other, or None when the sum would need more than two parameter terms."""
+        terms: dict = {}
+        for sl, cf in ((self.slot, self.coeff), (self.slot2, self.coeff2), (other.slot, sign * other.coeff), (other.slot2, sign * other.coeff2)):
+            if sl >= 0 and cf != 0.0:
+                terms[sl] = terms.get(sl, 0.0) + cf
+        terms = [(sl, cf) for sl, cf in terms.items() if cf != 0.0]
+        if len(terms) > 2:
+            return None
+        terms += [(-1, 0.0)] * (2 - len(terms))
+        return Angle(terms[0][0], terms[0][1], self.const + sign * other.const, terms[1][0], terms[1][1])
 
 
 ZERO = Angle()
@@ -89,6 +110,51 @@ class KernelOp:
         )
 
 
+def defer_phases(ops: Sequence[KernelOp], drop_final: bool = False) -> list[KernelOp]:
+    """Exact rewrite  e^{i gamma} U(theta, phi, lam) = e^{i gamma} D(phi) R_Y(theta) D(lam),  D(a) = diag(1, e^{ia}):  the trailing
+    D(phi) of every UNCONTROLLED dense gate is not applied but kept as a pending phase P_q on its qubit.  Diagonals commute
+    with controls and with each other, so the pending phase travels forward until
+      * the next uncontrolled dense gate on q absorbs it:     U(theta, phi, lam) D(P) = D(phi) [R_Y(theta) D(lam + P)]
+      * a controlled dense gate TARGETING q lets it through:  CU(theta, phi, lam) D_q(P) = D_q(P) CU(theta, phi - P, lam + P)
+      * the circuit ends: one DIAG op per qubit with a non-zero pending phase -- or nothing when ``drop_final`` (the caller
+        only needs |psi_k|^2: diagonal observables and sampling cannot see a diagonal phase).
+    Every emitted uncontrolled dense gate then has phi == 0: its matrix [[c, -s e^{i lam}], [s, c e^{i lam}]] has a real first
+    column and costs 12 instead of 14 multiply-adds per amplitude pair in the sweep kernel (REAL10 variants); `u -> u` chains
+    on a qubit never pay for the intermediate phase at all.  Angles stay affine in at most two parameters (the pending phase is
+    always the ORIGINAL phi of one gate); where a sum would need three, the pending phase is materialised as a DIAG op first."""
+    pending: dict[int, Angle] = {}
+    out: list[KernelOp] = []
+
+    def flush(q: int) -> None:
+        p = pending.pop(q, None)
+        if p is not None and not p.is_zero:
+            out.append(_diag(q, lam=p))
+
+    for op in ops:
+        if op.kind != DENSE:
+            out.append(op)  # diagonal on everything it touches: commutes with every pending phase
+            continue
+        t = op.target
+        p = pending.get(t, ZERO)
+        if op.control < 0:
+            lam = op.lam.plus(p)
+            if lam is None:
+                flush(t)
+                lam = op.lam
+            out.append(KernelOp(DENSE, t, -1, op.gamma, op.theta, ZERO, lam))
+            pending[t] = op.phi
+        else:
+            phi, lam = op.phi.plus(p, -1.0), op.lam.plus(p)
+            if phi is None or lam is None:
+                flush(t)
+                phi, lam = op.phi, op.lam
+            out.append(KernelOp(DENSE, t, op.control, op.gamma, op.theta, phi, lam))
+    if not drop_final:
+        for q in sorted(pending):
+            flush(q)
+    return out
+
+
 def dfma_per_amplitude(op: KernelOp) -> float:
     """FP64 multiply-add-class instructions per amplitude the sweep kernel spends on ``op`` (roofline accounting in bench.py):
     a dense 2x2 gate costs 16 per amplitude pair, 14 when its top-left entry is real (no global phase), 12 when the bottom-left
@@ -98,7 +164,7 @@ def dfma_per_amplitude(op: KernelOp) -> float:
         per = 4.0
     else:
         real00 = op.gamma.slot < 0 and op.gamma.const == 0.0
-        real10 = real00 and op.phi.slot < 0 and op.phi.const == 0.0 and not getattr(op, "phi2", None)
+        real10 = real00 and op.phi.is_zero and op.control < 0  # only the uncontrolled REAL10 bodies are compiled
         per = 6.0 if real10 else (7.0 if real00 else 8.0)
     return per * (1.0 if op.control < 0 else 0.5)
 

@@ -92,21 +92,23 @@ class _CircuitCache:
     def gates_for(self, circuit):
         return self._entry(circuit)
 
-    def plan_for(self, circuit, slot: int = 0, entry=None) -> Optional[PlanHandle]:
+    def plan_for(self, circuit, slot: int = 0, entry=None, probabilities_only: bool = False) -> Optional[PlanHandle]:
+        """``probabilities_only``: the caller needs |psi_k|^2 only (diagonal observable / sampling), so the plan may leave the
+        diagonal phases pending at the end of the circuit unapplied (engine.rewritten)."""
         entry = self._entry(circuit) if entry is None else entry
         if entry["gates"] is None:
             return None
-        plan = entry["plans"].get(slot)
+        plan = entry["plans"].get((slot, probabilities_only))
         if plan is None:
             # identity-cached circuits are the ones an optimizer loop re-submits: worth caching their constant prefix state
-            plan = self._engines[slot].compile_with_prefix_reuse(entry["gates"])
-            entry["plans"][slot] = plan
+            plan = self._engines[slot].compile_with_prefix_reuse(entry["gates"], drop_final_phases=probabilities_only)
+            entry["plans"][(slot, probabilities_only)] = plan
         return plan
 
-    def bound_plan(self, circuit, values, slot: int = 0) -> PlanHandle:
+    def bound_plan(self, circuit, values, slot: int = 0, probabilities_only: bool = False) -> PlanHandle:
         """Slow path for circuits whose angles are not affine in single parameters: bind on the host."""
         bound = circuit.assign_parameters(list(values)) if len(values) else circuit
-        return self._engines[slot].compile(from_circuit(bound))
+        return self._engines[slot].compile(from_circuit(bound), drop_final_phases=probabilities_only)
 
 
 def _rotate_for_process(devices: list) -> list:
@@ -265,7 +267,7 @@ class _B200Primitive:
                     entries[i]["home"] = best
         return out
 
-    def _resolve_all(self, circuits, parameter_values):
+    def _resolve_all(self, circuits, parameter_values, probabilities_only: bool = False):
         """-> list of (slot, plan, values) in submission order."""
         cache = self._cache
         entries = [cache.gates_for(c) for c in circuits]
@@ -276,10 +278,10 @@ class _B200Primitive:
         slots = self._assign(entries, costs)
         out = []
         for circuit, values, en, slot in zip(circuits, parameter_values, entries, slots):
-            plan = cache.plan_for(circuit, slot, en)
+            plan = cache.plan_for(circuit, slot, en, probabilities_only)
             if plan is None:
                 values = np.asarray(values if values is not None else (), dtype=np.float64).reshape(-1)
-                out.append((slot, cache.bound_plan(circuit, values, slot), np.zeros(0)))
+                out.append((slot, cache.bound_plan(circuit, values, slot, probabilities_only), np.zeros(0)))
             else:
                 # the float64 conversion happens chunk by chunk inside the engine's pipelined submission, overlapped with
                 # the GPU work of the previous chunk
@@ -365,7 +367,7 @@ class B200EstimatorV2(_B200Primitive):
             sizes.append(len(circs))
             circuits.extend(circs)
             values.extend(vals)
-        resolved = self._resolve_all(circuits, values)
+        resolved = self._resolve_all(circuits, values, probabilities_only=self.hamiltonian_for(operator).diagonal)
         flat = self._run_per_device(
             resolved, lambda slot, plans, params: self.engines[slot].expectation(plans, params, self.hamiltonian_for(operator, slot=slot))
         )
@@ -456,7 +458,7 @@ class B200SamplerV2(_B200Primitive):
             sizes.append(len(circs))
             circuits.extend(circs)
             values.extend(vals)
-        resolved = self._resolve_all(circuits, values)
+        resolved = self._resolve_all(circuits, values, probabilities_only=True)
         # a fresh default_rng(seed) per pub when seed is an int (or None); a shared Generator is consumed in submission order
         if isinstance(self.seed, np.random.Generator):
             uniforms = np.stack([self.seed.random(shots) for _ in resolved])

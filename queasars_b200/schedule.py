@@ -26,7 +26,7 @@ from typing import Sequence
 
 import numpy as np
 
-from .gate_list import DENSE, DIAG, KernelOp
+from .gate_list import DENSE, DIAG, KernelOp, dfma_per_amplitude
 
 TILE_BITS = 11  # default; 12 is also compiled (include/queasars_b200.h QB_MAX_TILE_BITS)
 REG_BITS = 4
@@ -43,6 +43,10 @@ PLAN_FULL_BUILDS = int(os.environ.get("QB_PLAN_FULL_BUILDS", "3"))  # how many o
 PLAN_VISIT_BUDGET = 400_000  # op visits the restarts may spend per circuit (48 trials up to ~8 000 op-sweeps)
 PLAN_ACCEPT = (0.9, 0.8, 0.7)  # probability of accepting a new tile qubit in a randomised trial (cycled over the trials)
 PREFER_CONTROLS_ON_WARP_BITS = os.environ.get("QB_CTRL_WARP", "1") != "0"  # A/B switch, see DESIGN.md
+# From this many (padded) qubits on a state sweep costs real HBM time, so a sweep whose FP64 work fits under its memory time is
+# free: spread the arithmetic evenly over the sweeps (without adding a sweep) instead of packing the first ones full.
+BALANCE_MIN_QUBITS = int(os.environ.get("QB_BALANCE_MIN_QUBITS", "22"))
+BALANCE_SLACK = (1.0, 1.1, 1.25, 1.5)
 
 # position kinds in the encoded program
 K_NONE, K_REG, K_THREAD, K_EXT = 0, 1, 2, 3
@@ -92,15 +96,18 @@ class CircuitPlan:
         return sum(len(s.passes) for s in self.sweeps)
 
 
-def _select_sweep(ops: Sequence[KernelOp], remaining: list[int], n_eff: int, k: int, low: int, max_ops: int, rng=None, p_accept: float = 1.0):
+def _select_sweep(ops: Sequence[KernelOp], remaining: list[int], n_eff: int, k: int, low: int, max_ops: int, rng=None, p_accept: float = 1.0,
+                  max_cost: float = float("inf")):
     """Greedy choice of one sweep: walk the remaining ops in circuit order, take every op that is not blocked by a deferred one
     and whose target is (or can still become) a tile qubit.  With ``rng`` a new tile qubit is only accepted with probability
-    ``p_accept`` -- the randomised restarts of ``plan_circuit`` use that to leave room for qubits with more work behind them."""
+    ``p_accept`` -- the randomised restarts of ``plan_circuit`` use that to leave room for qubits with more work behind them.
+    ``max_cost``: stop taking ops once the sweep's FP64 work (multiply-adds per amplitude) reaches it (sweep balancing)."""
     tile = set(range(min(low, n_eff)))
     pend_dense: set[int] = set()
     pend_any: set[int] = set()
     chosen: list[int] = []
     rest: list[int] = []
+    cost = 0.0
     for i in remaining:
         op = ops[i]
         t, c = op.target, op.control
@@ -108,7 +115,7 @@ def _select_sweep(ops: Sequence[KernelOp], remaining: list[int], n_eff: int, k: 
         blocked = (t in pend_any) if dense else (t in pend_dense)
         if c >= 0 and c in pend_dense:
             blocked = True
-        ok = not blocked and len(chosen) < max_ops
+        ok = not blocked and len(chosen) < max_ops and cost < max_cost
         if ok and dense and t not in tile:
             if len(tile) < k and (rng is None or rng.random() < p_accept):
                 tile.add(t)
@@ -116,6 +123,7 @@ def _select_sweep(ops: Sequence[KernelOp], remaining: list[int], n_eff: int, k: 
                 ok = False
         if ok:
             chosen.append(i)
+            cost += dfma_per_amplitude(op)
         else:
             rest.append(i)
             if dense:
@@ -324,14 +332,15 @@ def plan_circuit(
         init_ops, remaining = [-1] * n_qubits, list(range(len(ops)))
     init_ops = init_ops + [-1] * (n_eff - n_qubits)
 
-    def build(rng, p_accept: float = 1.0) -> list[SweepPlan]:
+    def build(rng, p_accept: float = 1.0, caps: Sequence[float] = ()) -> list[SweepPlan]:
         todo, out = list(remaining), []
         while todo:
             max_ops = MAX_SWEEP_OPS
+            cap = caps[len(out)] if len(out) < len(caps) else float("inf")
             while True:  # the kernel stages at most MAX_SWEEP_OPS matrices / MAX_SWEEP_PASSES pass records per sweep
-                tile_qubits, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, max_ops, rng, p_accept)
+                tile_qubits, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, max_ops, rng, p_accept, cap)
                 if not chosen:  # an unlucky draw accepted nothing: plain greedy always makes progress
-                    tile_qubits, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, max_ops)
+                    tile_qubits, chosen, rest = _select_sweep(ops, todo, n_eff, tile_bits, low_bits, max_ops, max_cost=cap)
                 passes = _plan_passes(ops, chosen, tile_qubits, reg_bits, low_bits)
                 if len(passes) <= MAX_SWEEP_PASSES or max_ops == 1:
                     break
@@ -377,10 +386,31 @@ def plan_circuit(
             return len(candidate), sum(len(sw.passes) for sw in candidate)
 
         # among the draws with the fewest sweeps the one with the fewest passes (= shared-memory exchanges) wins
+        winner = None
         for seed, p_accept in best:
             alt = build(random.Random(seed), p_accept)
             if cost(alt) < cost(sweeps):
-                sweeps = alt
+                sweeps, winner = alt, (seed, p_accept)
+        # Sweep balancing (HBM-resident states only): the greedy packs the early sweeps full and leaves the last ones nearly
+        # empty; a sweep costs max(HBM time, FP64 time), so the same number of sweeps with the arithmetic spread evenly is
+        # never slower and is faster whenever a light sweep can hide work under its memory time.  The first sweep of a
+        # product-state start only writes (half the HBM time): it gets half a share.
+        if n_eff >= BALANCE_MIN_QUBITS and len(sweeps) > 1:
+
+            def sweep_costs(candidate: list[SweepPlan]) -> list[float]:
+                return [sum(dfma_per_amplitude(ops[po.op_index]) for ps in sw.passes for po in ps.ops) for sw in candidate]
+
+            costs = sweep_costs(sweeps)
+            weights = [0.5 if (product_prefix and i == 0) else 1.0 for i in range(len(sweeps))]
+            total, wsum = sum(costs), sum(weights)
+            for slack in BALANCE_SLACK:
+                caps = [slack * total * w / wsum for w in weights]
+                if max(c / w for c, w in zip(costs, weights)) <= 1.05 * slack * total / wsum:
+                    break  # already at least this even
+                alt = build(random.Random(winner[0]) if winner else None, winner[1] if winner else 1.0, caps)
+                if len(alt) == len(sweeps):
+                    sweeps = alt
+                    break
     if not sweeps:  # empty circuit: one identity sweep so that |0...0> gets materialised
         tile_qubits = list(range(tile_bits))
         reg = list(range(tile_bits - reg_bits, tile_bits))
@@ -397,7 +427,10 @@ PASSOP_DTYPE = np.dtype(
     [("op_index", np.int32), ("kind", np.uint8), ("tgt_kind", np.uint8), ("tgt_pos", np.uint8), ("ctrl_kind", np.uint8), ("ctrl_pos", np.uint8), ("variant", np.uint8), ("ctrl_qubit", np.uint8), ("tgt_qubit", np.uint8)],
     align=True,
 )
-ANGLE_DTYPE = np.dtype([("slot", np.int32, (4,)), ("coeff", np.float64, (4,)), ("const", np.float64, (4,)), ("kind", np.int32), ("pad", np.int32)], align=True)
+ANGLE_DTYPE = np.dtype(
+    [("slot", np.int32, (4,)), ("slot2", np.int32, (4,)), ("coeff", np.float64, (4,)), ("coeff2", np.float64, (4,)), ("const", np.float64, (4,)), ("kind", np.int32), ("pad", np.int32)],
+    align=True,
+)
 
 
 def _predecode(po: PassOp, tile_qubits: Sequence[int]) -> tuple[int, int, int]:
@@ -451,6 +484,7 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
     for i, op in enumerate(ops):
         for j, a in enumerate(op.angles):
             angles[i]["slot"][j], angles[i]["coeff"][j], angles[i]["const"][j] = a.slot, a.coeff, a.const
+            angles[i]["slot2"][j], angles[i]["coeff2"][j] = a.slot2, a.coeff2
         angles[i]["kind"] = op.kind
     init_ops = np.asarray(plan.init_ops if plan.init_ops else [-1] * plan.n_eff, dtype=np.int32)
     return sweeps, passes, pass_ops, angles, init_ops

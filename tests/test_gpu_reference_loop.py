@@ -1,0 +1,82 @@
+"""The UNMODIFIED reference EVQE loop (``EVQEMinimumEigensolver.compute_minimum_eigenvalue``: population, speciation, mutation,
+NFT / SPSA optimizer chains, selection, final eigenstate -- /root/reference/queasars/minimum_eigensolvers/base/
+evolving_ansatz_minimum_eigensolver.py:227-260, 331-478) running on the B200 primitives handed to it inside
+``Configured*V2``: the drop-in route that edits nothing in the reference.  Skips only when the reference package is absent
+(on the GPU box it travels as the git-ignored ``baseline/_ref``; tools/stage_reference.py).  Outcomes asserted are the ones the
+reference's own test / notebook state: x^2 - y^2 -> [0, 3] (test_evqe_algorithm.py:36-38), 4-qubit JSSP -> 63.5."""
+import json
+import os
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import pytest
+
+from tests import reference_loop
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(reference_loop.locate_reference() is None, reason="reference package not present (baseline/_ref not staged)")]
+
+LOG = os.path.join(reference_loop.ROOT, "gpurun_out", "reference_loop_gpu.jsonl")
+
+
+def _log(entry):
+    try:
+        os.makedirs(os.path.dirname(LOG), exist_ok=True)
+        with open(LOG, "a") as fh:
+            fh.write(json.dumps(entry) + "\n")
+    except OSError:
+        pass
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return reference_loop.import_reference()
+
+
+@pytest.mark.parametrize("mutex", [False, True])
+def test_reference_evqe_on_b200_primitives_finds_ground_state(ref, mutex):
+    from queasars_b200 import B200EstimatorV2, B200SamplerV2
+
+    estimator, sampler = B200EstimatorV2(device=0, seed=2), B200SamplerV2(device=0, seed=1)
+    launches0 = estimator.engine.launch_count
+    with ThreadPoolExecutor(max_workers=10) as pool:
+        # mutex=True routes every call through the reference's BatchingMutex* wrappers (0.1 s batching sleep per call:
+        # mutex_primitives.py:119-121) -- one generation is enough to prove the contract there
+        solver = reference_loop.sample_solver(ref, estimator, sampler, pool, mutex=mutex, max_generations=1 if mutex else None)
+        t0 = time.perf_counter()
+        result = solver.compute_minimum_eigenvalue(operator=reference_loop.test_model_hamiltonian())
+        dt = time.perf_counter() - t0
+    launches = estimator.engine.launch_count - launches0
+    assert launches > 0, "the reference loop did not reach the CUDA engine"
+    evals = sum(result.circuit_evaluations)
+    _log({"case": "x2-y2 model, estimator + sampler", "mutex": mutex, "seconds": dt, "circuit_evaluations": evals, "evals_per_s": evals / dt,
+          "eigenvalue": float(result.eigenvalue), "best": reference_loop.likeliest_bitstring(result), "kernel_launches": launches,
+          "reference": ref["path"]})
+    if mutex:
+        assert result.eigenvalue < 0
+    else:
+        assert reference_loop.likeliest_bitstring(result) == "1100"  # x = 0, y = 3
+        assert result.eigenvalue == pytest.approx(-9.0, abs=0.5)
+        assert evals > 100
+
+
+def test_reference_evqe_jssp_4q_sampler_cvar_on_b200(ref):
+    """BASELINE config C1: the smallest JSSP instance of examples/evqe_jssp_small_examples.ipynb, sampler-only CVaR(0.5)
+    objective, the reference's loop unchanged, B200SamplerV2 underneath."""
+    from queasars_b200 import B200SamplerV2
+
+    encoder, hamiltonian = reference_loop.jssp_4q(ref)
+    assert encoder.n_qubits == 4
+    sampler = B200SamplerV2(device=0, seed=None)
+    launches0 = sampler.engine.launch_count
+    with ThreadPoolExecutor(max_workers=10) as pool:
+        solver = reference_loop.jssp_solver(ref, sampler, pool, random_seed=0)
+        t0 = time.perf_counter()
+        result = solver.compute_minimum_eigenvalue(operator=hamiltonian)
+        dt = time.perf_counter() - t0
+    evals = sum(result.circuit_evaluations)
+    best = reference_loop.likeliest_bitstring(result)
+    _log({"case": "C1: 4-qubit JSSP, sampler CVaR(0.5), SPSA", "seconds": dt, "circuit_evaluations": evals, "evals_per_s": evals / dt,
+          "eigenvalue": float(result.eigenvalue), "best": best, "kernel_launches": sampler.engine.launch_count - launches0, "reference": ref["path"]})
+    assert sampler.engine.launch_count > launches0
+    assert best in ("0011", "1100")
+    assert result.eigenvalue == pytest.approx(63.5, abs=1.0)

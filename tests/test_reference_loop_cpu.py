@@ -10,8 +10,9 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import pytest
 
-REFERENCE = "/root/reference"
-pytestmark = [pytest.mark.reference, pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")]
+from tests import reference_loop
+
+pytestmark = [pytest.mark.reference, pytest.mark.skipif(reference_loop.locate_reference() is None, reason="reference package not present (/root/reference or baseline/_ref)")]
 
 
 def _instructions(circuit):
@@ -71,59 +72,14 @@ class OracleSamplerV2:
 
 @pytest.fixture(scope="module")
 def reference_modules():
-    from queasars_b200 import qiskit_compat
-
-    qiskit_compat.install()
-    if REFERENCE not in sys.path:
-        sys.path.insert(0, REFERENCE)
-    from queasars.circuit_evaluation.configured_primitives import ConfiguredEstimatorV2, ConfiguredSamplerV2
-    from queasars.minimum_eigensolvers.base.termination_criteria import BestIndividualRelativeChangeTolerance
-    from queasars.minimum_eigensolvers.evqe.evqe import EVQEMinimumEigensolver, EVQEMinimumEigensolverConfiguration
-
-    return ConfiguredEstimatorV2, ConfiguredSamplerV2, BestIndividualRelativeChangeTolerance, EVQEMinimumEigensolver, EVQEMinimumEigensolverConfiguration
-
-
-def _hamiltonian():
-    from queasars_b200.operators import SparsePauliOp
-
-    return SparsePauliOp.from_list([("IIIZ", -1.5), ("IIZI", -3.0), ("IIZZ", 1.0), ("IZII", 1.5), ("ZIII", 3.0), ("ZZII", -1.0)])
-
-
-def _solver(mods, executor, mutex, max_generations=None):
-    ConfiguredEstimatorV2, ConfiguredSamplerV2, Criterion, Solver, Configuration = mods
-    from qiskit_algorithms.optimizers import NFT
-
-    configuration = Configuration(
-        configured_sampler=ConfiguredSamplerV2(sampler=OracleSamplerV2(seed=1), shots=1000),
-        configured_estimator=ConfiguredEstimatorV2(estimator=OracleEstimatorV2(seed=2), precision=0.05),
-        pass_manager=None,
-        optimizer=NFT(maxiter=40),
-        optimizer_n_circuit_evaluations=40,
-        max_generations=max_generations,
-        max_circuit_evaluations=None,
-        termination_criterion=None if max_generations else Criterion(minimum_relative_change=0.005),
-        random_seed=0,
-        population_size=10,
-        randomize_initial_population_parameters=False,
-        speciation_genetic_distance_threshold=3,
-        selection_alpha_penalty=0.1,
-        selection_beta_penalty=0.1,
-        parameter_search_probability=0.24,
-        topological_search_probability=0.2,
-        layer_removal_probability=0.05,
-        parallel_executor=executor,
-        mutually_exclusive_primitives=mutex,
-    )
-    return Solver(configuration=configuration)
+    return reference_loop.import_reference()
 
 
 def test_reference_evqe_finds_ground_state(reference_modules):
     with ThreadPoolExecutor(max_workers=4) as pool:
-        solver = _solver(reference_modules, pool, mutex=False)
-        result = solver.compute_minimum_eigenvalue(operator=_hamiltonian())
-    probs = result.eigenstate.binary_probabilities()
-    best = max(probs, key=probs.get)
-    assert best == "1100"  # x = 0, y = 3
+        solver = reference_loop.sample_solver(reference_modules, OracleEstimatorV2(seed=2), OracleSamplerV2(seed=1), pool, mutex=False)
+        result = solver.compute_minimum_eigenvalue(operator=reference_loop.test_model_hamiltonian())
+    assert reference_loop.likeliest_bitstring(result) == "1100"  # x = 0, y = 3
     assert result.eigenvalue == pytest.approx(-9.0, abs=0.5)
     assert result.circuit_evaluations and sum(result.circuit_evaluations) > 100
 
@@ -131,6 +87,6 @@ def test_reference_evqe_finds_ground_state(reference_modules):
 def test_reference_batching_mutex_wrappers_accept_the_contract(reference_modules):
     """One generation through BatchingMutex* + Transpiling* (0.1 s batching sleep per call: keep it short)."""
     with ThreadPoolExecutor(max_workers=10) as pool:
-        solver = _solver(reference_modules, pool, mutex=True, max_generations=1)
-        result = solver.compute_minimum_eigenvalue(operator=_hamiltonian())
+        solver = reference_loop.sample_solver(reference_modules, OracleEstimatorV2(seed=2), OracleSamplerV2(seed=1), pool, mutex=True, max_generations=1)
+        result = solver.compute_minimum_eigenvalue(operator=reference_loop.test_model_hamiltonian())
     assert result.eigenvalue < 0
