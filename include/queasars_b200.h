@@ -109,6 +109,8 @@ int64_t qb_context_launch_count(qb_context* ctx);
 int qb_context_sm_count(qb_context* ctx);
 /* Upper bound for statevector workspace (bytes); 0 = 80 % of the device memory free at creation. */
 int qb_context_set_workspace_limit(qb_context* ctx, uint64_t bytes);
+/* The limit in effect (bytes): a statevector larger than this does not fit one device and has to be sharded. */
+uint64_t qb_context_workspace(qb_context* ctx);
 /* Amplitude-index width of the sweep kernels: 32 = automatic (32-bit indices up to 31 local qubits, 64-bit above: the shards of
  * BASELINE config C5), 64 = always the 64-bit-index kernels, so that the kernels a 35-qubit sharded state runs can be checked
  * against the oracle at sizes the oracle finishes in seconds. */
@@ -222,6 +224,21 @@ int qb_sample_device(qb_context* ctx, int dtype, int n_local, const void* d_stat
  * rank touches its destination buffer. */
 int qb_swap_global_p2p(qb_context* ctx, int dtype, int n_local, const void* d_state, void* const* peer_dst, int world, int rank,
                        int n_global, const int32_t* local_positions);
+
+/* --- device memory and peer mapping for sharded states ----------------------------------------------------
+ * The shard buffers of a state sharded over several GPUs are plain cudaMalloc allocations owned by the engine of their device.
+ * Single process, several GPUs (the configuration behind evaluate_circuits): qb_enable_peer_access lets the swap kernel of
+ * one device store into the buffers of the others through their ordinary (unified) addresses.  One process per GPU: the owner
+ * exports a CUDA IPC handle (64 opaque bytes, sent to the peers by any means, e.g. a torch.distributed all_gather) and each
+ * peer maps the buffer with qb_ipc_open; the mapped address is what qb_swap_global_p2p takes in peer_dst[]. */
+int qb_device_alloc(qb_context* ctx, uint64_t bytes, void** out_ptr);
+int qb_device_free(qb_context* ctx, void* ptr);
+/* copy `bytes` from device address `src` (+ byte offset) to host memory; synchronises (tests, gathers of small states) */
+int qb_device_read(qb_context* ctx, const void* src, uint64_t offset, uint64_t bytes, void* host_out);
+int qb_enable_peer_access(qb_context* ctx, int peer_device); /* QB_OK also when access was already enabled or peer == own device */
+int qb_ipc_export(qb_context* ctx, void* ptr, unsigned char handle_out[64]);
+int qb_ipc_open(qb_context* ctx, const unsigned char handle[64], void** out_ptr);
+int qb_ipc_close(qb_context* ctx, void* mapped_ptr);
 
 /* layout self-check for language bindings: sizeof() of the four records above */
 void qb_record_sizes(int32_t out[4]);

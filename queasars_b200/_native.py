@@ -63,6 +63,13 @@ def _declare(lib):
         "qb_expectation_device": [c_void_p, c_int64, c_int, c_int, c_void_p, c_uint64, P(c_double)],
         "qb_sample_device": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
         "qb_swap_global_p2p": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+        "qb_device_alloc": [c_void_p, c_uint64, P(c_void_p)],
+        "qb_device_free": [c_void_p, c_void_p],
+        "qb_device_read": [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p],
+        "qb_enable_peer_access": [c_void_p, c_int],
+        "qb_ipc_export": [c_void_p, c_void_p, c_void_p],
+        "qb_ipc_open": [c_void_p, c_void_p, P(c_void_p)],
+        "qb_ipc_close": [c_void_p, c_void_p],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -70,6 +77,8 @@ def _declare(lib):
         fn.restype = c_int
     lib.qb_context_stream.restype = c_void_p
     lib.qb_context_launch_count.restype = c_int64
+    lib.qb_context_workspace.argtypes = [c_void_p]
+    lib.qb_context_workspace.restype = c_uint64
     lib.qb_last_error.argtypes = []
     lib.qb_last_error.restype = c_char_p
     lib.qb_record_sizes.argtypes = [P(c_int32)]
@@ -79,11 +88,12 @@ def _declare(lib):
 
 EXPORTED_SYMBOLS = (
     "qb_device_count qb_context_create qb_context_destroy qb_last_error qb_context_stream qb_context_launch_count "
-    "qb_context_set_workspace_limit qb_context_synchronize qb_context_set_index_width qb_plan_create qb_plan_destroy qb_plan_set_prefix qb_hamiltonian_create "
+    "qb_context_set_workspace_limit qb_context_workspace qb_context_synchronize qb_context_set_index_width qb_plan_create qb_plan_destroy qb_plan_set_prefix qb_hamiltonian_create "
     "qb_hamiltonian_destroy qb_hamiltonian_diag_energies qb_evaluate_expectation qb_sample qb_statevector "
     "qb_evaluate_expectation_submit qb_evaluate_expectation_collect qb_context_sm_count "
     "qb_batch_create qb_batch_set_params qb_batch_run qb_batch_run_timed qb_batch_read qb_batch_destroy qb_batch_stats "
-    "qb_apply_plan_device qb_expectation_device qb_sample_device qb_swap_global_p2p qb_record_sizes"
+    "qb_apply_plan_device qb_expectation_device qb_sample_device qb_swap_global_p2p qb_record_sizes "
+    "qb_device_alloc qb_device_free qb_device_read qb_enable_peer_access qb_ipc_export qb_ipc_open qb_ipc_close"
 ).split()
 
 

@@ -178,6 +178,11 @@ namespace {
 
 size_t amp_bytes(int dtype) { return dtype == QB_C128 ? 16 : 8; }
 
+// terms of one x-mask group staged in shared memory (24 B each, inside the default 48 KB); longer lists are read from global memory
+constexpr int kMaxStagedTerms = 2000;
+// diagonal terms per diag_table_kernel launch (16 B each in shared memory); longer lists build the table in several launches
+constexpr int kTableTermChunk = 3000;
+
 int set_device(qb_context* ctx) {
     QB_CUDA(cudaSetDevice(ctx->device));
     return QB_OK;
@@ -398,7 +403,7 @@ int expectation_state_t(qb_context* ctx, const Ham& ham, const void* d_state, in
     const int blocks = int(std::min<uint64_t>(1024, std::max<uint64_t>(1, size / 256)));
     bool first = true;
     if (ham.table.p && ham.table_n_eff == n_eff && index_offset == 0) {
-        qb::expect_table_kernel<T><<<blocks, 256, 0, ctx->stream>>>(static_cast<const C*>(d_state), ham.table.as<double>(), size, d_partials);
+        qb::expect_table_kernel<T><<<blocks, 256, 0, ctx->stream>>>(static_cast<const C*>(d_state), size, ham.table.as<double>(), size, d_partials, 0);
         QB_TRY(check_launch(ctx, "expect_table_kernel"));
         qb::reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(d_partials, blocks, blocks, d_out, 0);
         QB_TRY(check_launch(ctx, "reduce_partials_kernel"));
@@ -430,10 +435,11 @@ int expectation_state_t(qb_context* ctx, const Ham& ham, const void* d_state, in
         if (done[gi]) continue;
         if (g->xmask == 0 && !first && ham.table.p && ham.table_n_eff == n_eff && index_offset == 0) continue;  // diagonal part already taken from the table
         if (g->xmask >> n_eff) return fail(QB_ERR_INVALID, "Pauli term flips a qubit outside the local statevector");
-        const size_t smem = size_t(g->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double));
-        qb::expect_group_kernel<T><<<blocks, 256, smem, ctx->stream>>>(static_cast<const C*>(d_state), size, index_offset, g->xmask,
+        const bool stage = g->n_terms <= kMaxStagedTerms;
+        const size_t smem = stage ? size_t(g->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double)) : 0;
+        qb::expect_group_kernel<T><<<blocks, 256, smem, ctx->stream>>>(static_cast<const C*>(d_state), size, size, index_offset, g->xmask,
                                                                        g->z.as<uint64_t>(), g->wr.as<double>(), g->wi.as<double>(),
-                                                                       g->n_terms, d_partials);
+                                                                       g->n_terms, stage ? 1 : 0, d_partials, 0);
         QB_TRY(check_launch(ctx, "expect_group_kernel"));
         qb::reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(d_partials, blocks, blocks, d_out, first ? 0 : 1);
         QB_TRY(check_launch(ctx, "reduce_partials_kernel"));
@@ -464,16 +470,16 @@ template <typename T> int launch_expectation_t(qb_context* ctx, DeviceBatch& b) 
     } else if (ham.n_diag > 0) {
         const bool table = ham.table.p && ham.table_n_eff == b.n_eff;
         const Group* dg = ham.groups.front().get();  // the x == 0 group is stored first
-        for (int pos = 0; pos < b.batch; ++pos) {
-            if (table)
-                qb::expect_table_kernel<T><<<blocks, 256, 0, ctx->stream>>>(states + size * pos, ham.table.as<double>(), size,
-                                                                             partials + b.partial_stride * pos);
-            else
-                qb::expect_group_kernel<T><<<blocks, 256, size_t(dg->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double)), ctx->stream>>>(
-                    states + size * pos, size, 0, 0, dg->z.as<uint64_t>(), dg->wr.as<double>(), dg->wi.as<double>(), dg->n_terms,
-                    partials + b.partial_stride * pos);
-            QB_TRY(check_launch(ctx, "diagonal expectation kernel"));
+        const dim3 grid(unsigned(blocks), unsigned(b.batch));  // one launch for the whole batch
+        if (table) {
+            qb::expect_table_kernel<T><<<grid, 256, 0, ctx->stream>>>(states, size, ham.table.as<double>(), size, partials, b.partial_stride);
+        } else {
+            const bool stage = dg->n_terms <= kMaxStagedTerms;
+            qb::expect_group_kernel<T><<<grid, 256, stage ? size_t(dg->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double)) : 0, ctx->stream>>>(
+                states, size, size, 0, 0, dg->z.as<uint64_t>(), dg->wr.as<double>(), dg->wi.as<double>(), dg->n_terms, stage ? 1 : 0, partials,
+                b.partial_stride);
         }
+        QB_TRY(check_launch(ctx, "diagonal expectation kernel"));
         QB_TRY(reduce(blocks));
     }
     // ---- non-diagonal groups that fit a tile: one read of every state per tile sweep
@@ -498,12 +504,11 @@ template <typename T> int launch_expectation_t(qb_context* ctx, DeviceBatch& b) 
     for (int gi : generic) {
         const Group* g = ham.groups[gi].get();
         if (g->xmask >> b.n_eff) return fail(QB_ERR_INVALID, "Pauli term flips a qubit outside the statevector");
-        for (int pos = 0; pos < b.batch; ++pos) {
-            qb::expect_group_kernel<T><<<blocks, 256, size_t(g->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double)), ctx->stream>>>(
-                states + size * pos, size, 0, g->xmask, g->z.as<uint64_t>(), g->wr.as<double>(), g->wi.as<double>(), g->n_terms,
-                partials + b.partial_stride * pos);
-            QB_TRY(check_launch(ctx, "expect_group_kernel"));
-        }
+        const bool stage = g->n_terms <= kMaxStagedTerms;
+        qb::expect_group_kernel<T><<<dim3(unsigned(blocks), unsigned(b.batch)), 256, stage ? size_t(g->n_terms) * (sizeof(uint64_t) + 2 * sizeof(double)) : 0,
+                                     ctx->stream>>>(states, size, size, 0, g->xmask, g->z.as<uint64_t>(), g->wr.as<double>(), g->wi.as<double>(), g->n_terms,
+                                                    stage ? 1 : 0, partials, b.partial_stride);
+        QB_TRY(check_launch(ctx, "expect_group_kernel"));
         QB_TRY(reduce(blocks));
     }
     if (!have) QB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * size_t(b.batch), ctx->stream));
@@ -818,12 +823,13 @@ int qb_hamiltonian_create(qb_context* ctx, int n_qubits, int n_terms, const uint
         const uint64_t size = uint64_t(1) << n_eff;
         QB_TRY(ham->table.reserve(sizeof(double) * size));
         ham->table_n_eff = n_eff;
-        const size_t smem = size_t(ham->n_diag) * (sizeof(uint64_t) + sizeof(double));
-        if (smem > 48 * 1024) return fail(QB_ERR_INVALID, "too many diagonal terms for the table builder");
         const int blocks = int(std::min<uint64_t>(uint64_t(ctx->sm_count) * 8, std::max<uint64_t>(1, size / 256)));
-        qb::diag_table_kernel<<<blocks, 256, smem, ctx->stream>>>(ham->table.as<double>(), size, 0, ham->diag_z.as<uint64_t>(),
-                                                                  ham->diag_c.as<double>(), ham->n_diag);
-        QB_TRY(check_launch(ctx, "diag_table_kernel"));
+        for (int lo = 0; lo < ham->n_diag; lo += kTableTermChunk) {  // term order is kept: chunk after chunk accumulates onto the table
+            const int cnt = std::min(kTableTermChunk, ham->n_diag - lo);
+            qb::diag_table_kernel<<<blocks, 256, size_t(cnt) * (sizeof(uint64_t) + sizeof(double)), ctx->stream>>>(
+                ham->table.as<double>(), size, 0, ham->diag_z.as<uint64_t>() + lo, ham->diag_c.as<double>() + lo, cnt, lo ? 1 : 0);
+            QB_TRY(check_launch(ctx, "diag_table_kernel"));
+        }
         QB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     {   // schedule the non-diagonal x-mask groups into tile sweeps
@@ -1291,5 +1297,91 @@ int qb_evaluate_expectation_collect(qb_context* ctx, int total, double* out_valu
 }
 
 int qb_context_sm_count(qb_context* ctx) { return ctx ? ctx->sm_count : 0; }
+
+uint64_t qb_context_workspace(qb_context* ctx) { return ctx ? (ctx->workspace_limit ? ctx->workspace_limit : ctx->default_workspace) : 0; }
+
+// ---- device memory / peer mapping for sharded states --------------------------------------------------
+int qb_device_alloc(qb_context* ctx, uint64_t bytes, void** out_ptr) {
+    if (!ctx || !out_ptr || !bytes) return fail(QB_ERR_INVALID, "null argument / zero size");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, size_t(bytes));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(QB_ERR_MEMORY, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    *out_ptr = p;
+    return QB_OK;
+}
+
+int qb_device_free(qb_context* ctx, void* ptr) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    if (!ptr) return QB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    QB_CUDA(cudaFree(ptr));
+    return QB_OK;
+}
+
+int qb_device_read(qb_context* ctx, const void* src, uint64_t offset, uint64_t bytes, void* host_out) {
+    if (!ctx || !src || !host_out) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    QB_CUDA(cudaMemcpyAsync(host_out, static_cast<const unsigned char*>(src) + offset, size_t(bytes), cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QB_OK;
+}
+
+int qb_enable_peer_access(qb_context* ctx, int peer_device) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    if (peer_device == ctx->device) return QB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    int can = 0;
+    QB_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return fail(QB_ERR_CUDA, "device " + std::to_string(ctx->device) + " cannot map the memory of device " + std::to_string(peer_device) + " (no peer access)");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return QB_OK;
+    }
+    if (e != cudaSuccess) return fail(QB_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    return QB_OK;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+
+int qb_ipc_export(qb_context* ctx, void* ptr, unsigned char handle_out[64]) {
+    if (!ctx || !ptr || !handle_out) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    cudaIpcMemHandle_t h;
+    QB_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    std::memcpy(handle_out, &h, 64);
+    return QB_OK;
+}
+
+int qb_ipc_open(qb_context* ctx, const unsigned char handle[64], void** out_ptr) {
+    if (!ctx || !handle || !out_ptr) return fail(QB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    QB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *out_ptr = p;
+    return QB_OK;
+}
+
+int qb_ipc_close(qb_context* ctx, void* mapped_ptr) {
+    if (!ctx) return fail(QB_ERR_INVALID, "null context");
+    if (!mapped_ptr) return QB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    QB_TRY(set_device(ctx));
+    QB_CUDA(cudaIpcCloseMemHandle(mapped_ptr));
+    return QB_OK;
+}
 
 }  // extern "C"

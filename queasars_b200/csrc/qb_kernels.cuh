@@ -649,15 +649,20 @@ __device__ __forceinline__ double diag_energy(uint64_t k, const uint64_t* __rest
     return e;
 }
 
+// `accumulate`: add onto the table (term lists longer than the shared-memory staging are built chunk by chunk, in term order)
 __global__ void diag_table_kernel(double* __restrict__ table, uint64_t size, uint64_t index_offset,
-                                  const uint64_t* __restrict__ z, const double* __restrict__ c, int n_terms) {
+                                  const uint64_t* __restrict__ z, const double* __restrict__ c, int n_terms, int accumulate) {
     extern __shared__ unsigned char dsm[];
     uint64_t* sz = reinterpret_cast<uint64_t*>(dsm);
     double* sc = reinterpret_cast<double*>(sz + n_terms);
     for (int t = threadIdx.x; t < n_terms; t += blockDim.x) sz[t] = z[t], sc[t] = c[t];
     __syncthreads();
-    for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x)
-        table[k] = diag_energy(k | index_offset, sz, sc, n_terms);
+    for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x) {
+        double e = accumulate ? table[k] : 0.0;
+        const uint64_t kk = k | index_offset;
+        for (int t = 0; t < n_terms; ++t) e += (__popcll(kk & sz[t]) & 1) ? -sc[t] : sc[t];
+        table[k] = e;
+    }
 }
 
 __global__ void diag_lookup_kernel(const uint64_t* __restrict__ states, int64_t n_states, const uint64_t* __restrict__ z,
@@ -668,32 +673,40 @@ __global__ void diag_lookup_kernel(const uint64_t* __restrict__ states, int64_t 
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-expect_table_kernel(const typename Cx<T>::type* __restrict__ state, const double* __restrict__ table, uint64_t size,
-                    double* __restrict__ partials) {
+expect_table_kernel(const typename Cx<T>::type* __restrict__ states, uint64_t state_stride, const double* __restrict__ table, uint64_t size,
+                    double* __restrict__ partials, uint64_t partial_stride) {
     __shared__ double s_red[8];
+    const auto* state = states + blockIdx.y * state_stride;  // grid.y = batch entry
     double acc = 0.0;
     for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x) {
         const auto a = state[k];
         acc += (double(a.x) * double(a.x) + double(a.y) * double(a.y)) * table[k];
     }
     const double total = block_sum(acc, s_red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+    if (threadIdx.x == 0) partials[blockIdx.y * partial_stride + blockIdx.x] = total;
 }
 
 // One x-mask group of a Pauli sum:  sum_k Re[ psi_k conj(psi_{k^x}) W(k) ],  W(k) = sum_t w_t (-1)^{pc(k & z_t)},
 // w_t = coeff_t * i^{#Y_t}.  x == 0 is the diagonal group evaluated on the fly.
 template <typename T>
 __global__ void __launch_bounds__(256)
-expect_group_kernel(const typename Cx<T>::type* __restrict__ state, uint64_t size, uint64_t index_offset, uint64_t xmask,
-                    const uint64_t* __restrict__ z, const double* __restrict__ wr, const double* __restrict__ wi, int n_terms,
-                    double* __restrict__ partials) {
+expect_group_kernel(const typename Cx<T>::type* __restrict__ states, uint64_t state_stride, uint64_t size, uint64_t index_offset, uint64_t xmask,
+                    const uint64_t* __restrict__ z, const double* __restrict__ wr, const double* __restrict__ wi, int n_terms, int stage_terms,
+                    double* __restrict__ partials, uint64_t partial_stride) {
     extern __shared__ unsigned char dsm[];
-    uint64_t* sz = reinterpret_cast<uint64_t*>(dsm);
-    double* swr = reinterpret_cast<double*>(sz + n_terms);
-    double* swi = swr + n_terms;
     __shared__ double s_red[8];
-    for (int t = threadIdx.x; t < n_terms; t += blockDim.x) sz[t] = z[t], swr[t] = wr[t], swi[t] = wi[t];
-    __syncthreads();
+    const auto* state = states + blockIdx.y * state_stride;  // grid.y = batch entry
+    // terms staged in shared memory while they fit (stage_terms); longer lists are read from global memory (L1 / L2 resident)
+    const uint64_t* sz = z;
+    const double *swr = wr, *swi = wi;
+    if (stage_terms) {
+        uint64_t* tz = reinterpret_cast<uint64_t*>(dsm);
+        double* twr = reinterpret_cast<double*>(tz + n_terms);
+        double* twi = twr + n_terms;
+        for (int t = threadIdx.x; t < n_terms; t += blockDim.x) tz[t] = z[t], twr[t] = wr[t], twi[t] = wi[t];
+        __syncthreads();
+        sz = tz, swr = twr, swi = twi;
+    }
     double acc = 0.0;
     for (uint64_t k = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; k < size; k += uint64_t(gridDim.x) * blockDim.x) {
         const auto a = state[k];
@@ -710,7 +723,7 @@ expect_group_kernel(const typename Cx<T>::type* __restrict__ state, uint64_t siz
         acc += pr * Wr - pi * Wi;
     }
     const double total = block_sum(acc, s_red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+    if (threadIdx.x == 0) partials[blockIdx.y * partial_stride + blockIdx.x] = total;
 }
 
 // ---------------------------------------------------------------------------------------------------

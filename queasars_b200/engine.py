@@ -98,6 +98,25 @@ def operator_terms(operator):
     return op.num_qubits, x, z, c
 
 
+def merge_duplicate_terms(x, z, c):
+    """Sum the coefficients of identical (x, z) Pauli strings, keeping first-appearance order (the reference's JSSP encoder emits
+    346 raw terms for 84 distinct strings at 26 qubits: job_shop_scheduling/domain_wall_hamiltonian_encoder.py:189-230)."""
+    x = np.asarray(x, dtype=np.uint64)
+    z = np.asarray(z, dtype=np.uint64)
+    c = np.asarray(c, dtype=complex)
+    if x.size < 2:
+        return x, z, c
+    keys = np.stack([x, z], axis=1)
+    uniq, first, inverse = np.unique(keys, axis=0, return_index=True, return_inverse=True)
+    if len(uniq) == x.size:
+        return x, z, c
+    inverse = np.asarray(inverse).reshape(-1)
+    summed = np.zeros(len(uniq), dtype=complex)
+    np.add.at(summed, inverse, c)
+    order = np.argsort(first)
+    return uniq[order, 0].copy(), uniq[order, 1].copy(), summed[order]
+
+
 def pipeline_split_point(n: int, n_eff: int, tile_bits: int, sm_count: int) -> Optional[int]:
     """First-chunk size of the two-chunk pipelined submission of ``n`` evaluations of ``n_eff``-qubit states: the split (between
     a fifth and half of the list) that wastes the fewest partially filled waves of sweep CTAs -- a state contributes
@@ -158,6 +177,11 @@ class Engine:
 
     def synchronize(self):
         _native.check(self._lib.qb_context_synchronize(self._ctx))
+
+    @property
+    def workspace_bytes(self) -> int:
+        """Statevector workspace of this device; a state larger than this has to be sharded over several GPUs."""
+        return int(self._lib.qb_context_workspace(self._ctx))
 
     def set_index_width(self, bits: int):
         """64: run the 64-bit-index sweep kernels (what > 31 local qubits use) at any size; 32: automatic."""
@@ -235,15 +259,20 @@ class Engine:
 
     def hamiltonian(self, operator, build_table: Optional[bool] = None) -> HamiltonianHandle:
         n, x, z, c = operator_terms(operator)
+        x, z, c = merge_duplicate_terms(x, z, c)  # the reference's encoders emit each (x, z) string many times over
         x = np.ascontiguousarray(x, dtype=np.uint64)
         z = np.ascontiguousarray(z, dtype=np.uint64)
         cre = np.ascontiguousarray(c.real, dtype=np.float64)
         cim = np.ascontiguousarray(c.imag, dtype=np.float64)
         diagonal = not bool(np.any(x))
         n_diag = int(np.count_nonzero(x == 0))
+        table_bytes = 8 << max(n, self.tile_bits)
         if build_table is None:
-            # a table costs 8 B * 2^n once and turns the per-amplitude cost from O(terms) into one load
-            build_table = n_diag > 8 and n <= 32
+            # a table costs 8 B * 2^n once and turns the per-amplitude cost from O(terms) into one load; above a sixteenth of
+            # the statevector workspace (30 qubits on a 180 GB B200) the terms are evaluated on the fly instead
+            build_table = n_diag > 8 and table_bytes <= self.workspace_bytes // 16
+        elif build_table and table_bytes > self.workspace_bytes // 2:
+            raise ValueError(f"a diagonal table of {table_bytes >> 30} GiB does not fit next to the statevector workspace ({self.workspace_bytes >> 30} GiB)")
         ham_id = c_int64()
         _native.check(
             self._lib.qb_hamiltonian_create(self._ctx, n, len(cre), _native.ptr(x), _native.ptr(z), _native.ptr(cre), _native.ptr(cim), int(bool(build_table)), byref(ham_id))
@@ -373,6 +402,38 @@ class Engine:
         ptrs = np.asarray([int(p) for p in peer_ptrs], dtype=np.uint64)
         lp = np.asarray(list(local_positions), dtype=np.int32)
         _native.check(self._lib.qb_swap_global_p2p(self._ctx, _dtype_code(dtype), int(n_local), c_void_p(state_ptr), _native.ptr(ptrs), world, int(rank), len(lp), _native.ptr(lp)))
+
+    # ------------------------------------------------------------------ device memory / peer mapping (sharded states)
+    def device_alloc(self, nbytes: int) -> int:
+        out = c_void_p()
+        _native.check(self._lib.qb_device_alloc(self._ctx, int(nbytes), byref(out)))
+        return int(out.value)
+
+    def device_free(self, ptr: int):
+        if self._finalizer.alive:
+            _native.check(self._lib.qb_device_free(self._ctx, c_void_p(ptr)))
+
+    def device_read(self, ptr: int, offset: int, out: np.ndarray):
+        _native.check(self._lib.qb_device_read(self._ctx, c_void_p(ptr), int(offset), int(out.nbytes), _native.ptr(out)))
+        return out
+
+    def enable_peer_access(self, peer_device: int):
+        _native.check(self._lib.qb_enable_peer_access(self._ctx, int(peer_device)))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = (ctypes.c_ubyte * 64)()
+        _native.check(self._lib.qb_ipc_export(self._ctx, c_void_p(ptr), buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        out = c_void_p()
+        _native.check(self._lib.qb_ipc_open(self._ctx, buf, byref(out)))
+        return int(out.value)
+
+    def ipc_close(self, ptr: int):
+        if self._finalizer.alive:
+            _native.check(self._lib.qb_ipc_close(self._ctx, c_void_p(ptr)))
 
     def sample_device(self, dtype, n_local: int, state_ptr: int, uniforms: np.ndarray) -> np.ndarray:
         """searchsorted(cumsum(|psi|^2) / sum, uniforms, side='right') on a caller-owned device state (a shard)."""

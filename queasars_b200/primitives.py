@@ -132,8 +132,11 @@ class _B200Primitive:
     mapped onto several GPUs behind the unchanged evaluator interface; the evaluations are independent, so there is no
     collective."""
 
-    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, coalesce: bool = True, devices=None):
+    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, coalesce: bool = True, devices=None, shard_min_qubits: Optional[int] = None):
         self.device, self.dtype, self.seed, self.coalesce = int(device), str(np.dtype(dtype).name), seed, bool(coalesce)
+        # circuits of at least this many qubits are evaluated as ONE statevector sharded over the device set (sharded.py);
+        # None = as soon as the state does not fit one device's workspace (34 qubits complex128 on a 180 GB B200)
+        self.shard_min_qubits = None if shard_min_qubits is None else int(shard_min_qubits)
         if devices is not None and devices != "all":
             devices = [int(d) for d in devices]
             if not devices or len(set(devices)) != len(devices):
@@ -148,6 +151,7 @@ class _B200Primitive:
         self._ham_cache: dict = {}
         self._queue_obj: Optional[CoalescingQueue] = None
         self._pool_obj = None
+        self._sharded_obj: dict = {}
         self._lock = threading.Lock()
         self._rr = 0  # round-robin start of the device choice for small submissions
 
@@ -157,7 +161,7 @@ class _B200Primitive:
         import os
 
         return {"device": self.device, "dtype": self.dtype, "seed": self.seed, "coalesce": self.coalesce, "devices": self.devices,
-                "_origin_pid": self._origin_pid or os.getpid()}
+                "shard_min_qubits": self.shard_min_qubits, "_origin_pid": self._origin_pid or os.getpid()}
 
     def __setstate__(self, state):
         self.__dict__.update(state)
@@ -319,6 +323,51 @@ class _B200Primitive:
     def devices_used(self) -> list:
         return [e.device for e in self.engines]
 
+    # ------------------------------------------------------------------ circuits too wide for one GPU
+    def _needs_sharding(self, n_qubits: int) -> bool:
+        if self.shard_min_qubits is not None:
+            return n_qubits >= self.shard_min_qubits
+        amp = 16 if self.dtype == "complex128" else 8
+        return (amp << n_qubits) > self.engine.workspace_bytes
+
+    def _sharded_state(self, n_qubits: int):
+        """One state of ``n_qubits`` sharded over the largest power-of-two prefix of the device set (kept between calls: two
+        shard-sized buffers per GPU).  BASELINE config C5: 35 qubits over 8 GPUs."""
+        from .sharded import LocalShardedStatevector
+
+        if self.dtype != "complex128":
+            raise NotImplementedError("sharded statevectors are complex128")
+        with self._lock:
+            sv = self._sharded_obj.get(n_qubits)
+        if sv is not None:
+            return sv
+        engines = self.engines
+        count = 1 << int(np.log2(len(engines)))
+        if count < 2 and self.shard_min_qubits is None:
+            raise ValueError(
+                f"a {n_qubits}-qubit statevector does not fit one GPU ({self.engine.workspace_bytes >> 30} GiB workspace): "
+                "give the primitive a device set (devices=[...] or 'all') to shard it"
+            )
+        with self._lock:
+            for old in self._sharded_obj.values():  # one resident sharded state at a time: they are sized for most of the memory
+                old.close()
+            self._sharded_obj.clear()
+        sv = LocalShardedStatevector(n_qubits, engines[:count], min_local=min(12, n_qubits - int(np.log2(count))))
+        with self._lock:
+            self._sharded_obj[n_qubits] = sv
+        return sv
+
+    def _bound_gates(self, circuit, values):
+        """(gate list, parameter values) of one evaluation for the sharded route."""
+        entry = self._cache.gates_for(circuit)
+        values = np.asarray(values if values is not None else (), dtype=np.float64).reshape(-1)
+        if entry["gates"] is not None:
+            if values.size != entry["gates"].n_params:
+                raise ValueError(f"circuit has {entry['gates'].n_params} parameters but {values.size} values were given")
+            return entry["gates"], values
+        bound = circuit.assign_parameters(list(values)) if len(values) else circuit
+        return from_circuit(bound), np.zeros(0)
+
     def _submit(self, key, payload):
         if self.coalesce:
             return self._queue.submit(key, payload)
@@ -343,8 +392,9 @@ def _param_rows(values) -> tuple[np.ndarray, tuple]:
 class B200EstimatorV2(_B200Primitive):
     """EstimatorV2-contract primitive backed by the CUDA statevector engine."""
 
-    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, default_precision: float = 0.0, coalesce: bool = True, devices=None):
-        super().__init__(device, dtype, seed, coalesce, devices)
+    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, default_precision: float = 0.0, coalesce: bool = True, devices=None,
+                 shard_min_qubits: Optional[int] = None):
+        super().__init__(device, dtype, seed, coalesce, devices, shard_min_qubits)
         self.default_precision = default_precision
 
     def __getstate__(self):
@@ -357,7 +407,8 @@ class B200EstimatorV2(_B200Primitive):
             raise ValueError(f"{len(circuits)} circuits but {len(parameter_values)} parameter vectors")
         if not circuits:
             return np.zeros(0)
-        self.hamiltonian_for(operator)  # validates the operator (and builds its device form) before anything is queued
+        if not self._needs_sharding(int(operator.num_qubits)):
+            self.hamiltonian_for(operator)  # validates the operator (and builds its device form) before anything is queued
         return np.asarray(self._submit(("exp", id(operator), _operator_fingerprint(operator)), (operator, circuits, parameter_values)))
 
     def _execute(self, key, payloads):
@@ -367,6 +418,20 @@ class B200EstimatorV2(_B200Primitive):
             sizes.append(len(circs))
             circuits.extend(circs)
             values.extend(vals)
+        if self._needs_sharding(int(operator.num_qubits)):
+            # one statevector over the whole device set, circuit after circuit (sharded.py): same values, no batch
+            sv = self._sharded_state(int(operator.num_qubits))
+            flat = []
+            for circuit, vals in zip(circuits, values):
+                gates, bound = self._bound_gates(circuit, vals)
+                sv.reset()
+                sv.run(gates, bound)
+                flat.append(sv.expectation(operator))
+            out, pos = [], 0
+            for n in sizes:
+                out.append(np.asarray(flat[pos : pos + n], dtype=np.float64))
+                pos += n
+            return out
         resolved = self._resolve_all(circuits, values, probabilities_only=self.hamiltonian_for(operator).diagonal)
         flat = self._run_per_device(
             resolved, lambda slot, plans, params: self.engines[slot].expectation(plans, params, self.hamiltonian_for(operator, slot=slot))
@@ -431,8 +496,9 @@ def _check_measure_all(circuit) -> None:
 class B200SamplerV2(_B200Primitive):
     """SamplerV2-contract primitive: shots drawn on the GPU from the exact statevector distribution."""
 
-    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, default_shots: int = 1024, coalesce: bool = True, devices=None):
-        super().__init__(device, dtype, seed, coalesce, devices)
+    def __init__(self, device: int = 0, dtype: str = "complex128", seed=None, default_shots: int = 1024, coalesce: bool = True, devices=None,
+                 shard_min_qubits: Optional[int] = None):
+        super().__init__(device, dtype, seed, coalesce, devices, shard_min_qubits)
         self.default_shots = default_shots
 
     def __getstate__(self):
@@ -458,6 +524,20 @@ class B200SamplerV2(_B200Primitive):
             sizes.append(len(circs))
             circuits.extend(circs)
             values.extend(vals)
+        if self._needs_sharding(key[2]):
+            sv = self._sharded_state(key[2])
+            rows = []
+            for circuit, vals in zip(circuits, values):
+                gates, bound = self._bound_gates(circuit, vals)
+                sv.reset()
+                sv.run(gates, bound)
+                rng = self.seed if isinstance(self.seed, np.random.Generator) else np.random.default_rng(self.seed)
+                rows.append(sv.sample(shots, uniforms=rng.random(shots)))
+            out, pos = [], 0
+            for n in sizes:
+                out.append(np.stack(rows[pos : pos + n]))
+                pos += n
+            return out
         resolved = self._resolve_all(circuits, values, probabilities_only=True)
         # a fresh default_rng(seed) per pub when seed is an int (or None); a shared Generator is consumed in submission order
         if isinstance(self.seed, np.random.Generator):

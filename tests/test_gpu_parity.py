@@ -555,3 +555,26 @@ def test_prefix_state_reuse_matches_full_evaluation(engine):
         idx = engine.sample([reuse], [batch[0]], 2000, np.random.default_rng(1).random((1, 2000)))[0]
         want = oq.sample_indices(oq.statevector(instr, n, batch[0]), 2000, uniforms=np.random.default_rng(1).random(2000))
         assert np.count_nonzero(idx != want) <= 1
+
+
+def test_term_counts_beyond_the_shared_memory_staging(engine):
+    """Operators with more terms than one launch stages in shared memory (3 000 diagonal terms per table-builder launch, 2 000
+    terms per x-mask group) and with duplicate strings (merged on the host): the reference accepts arbitrary SparsePauliOps."""
+    n = 14
+    rng = np.random.default_rng(77)
+    zs = rng.choice(1 << n, size=5000, replace=False)
+    diag = [(int(z), float(c)) for z, c in zip(zs, rng.normal(size=5000))]
+    diag += diag[:300]  # duplicates: coefficients add up
+    xmask = 0b101 << 5
+    group = [(int(z), complex(a, b)) for z, a, b in zip(rng.choice(1 << n, size=2500, replace=False), rng.normal(size=2500), rng.normal(size=2500))]
+    op_diag = SparsePauliOp._raw(n, [0] * len(diag), [z for z, _ in diag], [c for _, c in diag])
+    op_full = SparsePauliOp._raw(n, [0] * len(diag) + [xmask] * len(group), [z for z, _ in diag] + [z for z, _ in group], [c for _, c in diag] + [c for _, c in group])
+    instr, values, circ = evqe_case(n, 3, 5)
+    plan = engine.compile(gl.from_circuit(circ))
+    state = oq.statevector(instr, n, values)
+    want_diag = float(np.dot(np.abs(state) ** 2, oq.diagonal_table(n, diag)))
+    for build_table in (True, False):
+        got = engine.expectation([plan, plan], [values, values], engine.hamiltonian(op_diag, build_table=build_table))
+        assert rel_err(got[0], want_diag) < 1e-10 and got[0] == got[1]
+    want_full = oq.estimator_expectation(state, op_full.to_list())
+    assert rel_err(engine.expectation([plan], [values], engine.hamiltonian(op_full))[0], want_full) < 1e-10
