@@ -32,11 +32,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build_native(force: bool = False, verbose: bool = False, defines: tuple = (), out_path: str = LIB_PATH) -> str:
+    """``defines`` / ``out_path``: A/B builds of kernel variants (tools/build_variants.py); the product library has none."""
+    if not force and not needs_build() and out_path == LIB_PATH:
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB_PATH, *SOURCES]
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", os.path.join(ROOT, "include"), "-o", out_path, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)
@@ -44,7 +45,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out_path
 
 
 if __name__ == "__main__":

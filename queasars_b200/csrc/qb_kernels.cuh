@@ -24,6 +24,16 @@
 
 namespace qb {
 
+// Build-time experiment switches (defaults are the measured best; tools/build_variants.py builds A/B libraries):
+//   QB_SWEEP_CTAS   resident sweep CTAs per SM with 2^11-amplitude tiles (4 -> 128 registers per thread, 3 -> 168)
+//   QB_DENSE_GROUP  amplitude pairs of a dense gate advanced together, stage by stage (independent FP64 chains per warp = 4 x this)
+#ifndef QB_SWEEP_CTAS
+#define QB_SWEEP_CTAS 4
+#endif
+#ifndef QB_DENSE_GROUP
+#define QB_DENSE_GROUP 1
+#endif
+
 constexpr int kMaxSweepOps = 96;
 constexpr int kMaxSweepPasses = 16;
 
@@ -114,34 +124,71 @@ template <typename T, int R, int B, int CB, bool REAL00 = false, bool REAL10 = f
 __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type m00, const typename Cx<T>::type m01,
                                             const typename Cx<T>::type m10, const typename Cx<T>::type m11) {
     constexpr int kNReg = 1 << R;
+    constexpr int kPairs = (CB >= 0) ? kNReg / 4 : kNReg / 2;
+    constexpr int G = (QB_DENSE_GROUP < kPairs) ? QB_DENSE_GROUP : kPairs;
     using C = typename Cx<T>::type;
+    // compile-time list of the pair bases this gate touches (register index with bit B clear, and bit CB set when controlled)
+    int base[kPairs];
+    {
+        int n = 0;
 #pragma unroll
-    for (int j = 0; j < kNReg; ++j) {
-        if (j & (1 << B)) continue;
-        if (CB >= 0 && !(j & (1 << (CB >= 0 ? CB : 0)))) continue;
-        // Term order chosen so that the last FMA of each output reads exactly the register it overwrites:
-        // the update is in place with four temporaries and no register moves at loop / switch merge points.
-        const C x = a[j], y = a[j | (1 << B)];
-        T t0 = m01.x * y.x;
-        T t1 = m01.x * y.y;
-        T t2 = m10.x * x.x;
-        T t3 = m10.x * x.y;
-        t0 = fma(-m01.y, y.y, t0);
-        t1 = fma(m01.y, y.x, t1);
+        for (int j = 0; j < kNReg; ++j) {
+            if (j & (1 << B)) continue;
+            if (CB >= 0 && !(j & (1 << (CB >= 0 ? CB : 0)))) continue;
+            base[n++] = j;
+        }
+    }
+    // Term order chosen so that the last FMA of each output reads exactly the register it overwrites: the update is in place
+    // with four temporaries per pair and no register moves at loop / switch merge points.  G pairs advance together, one
+    // multiply-add stage at a time, so a warp carries 4 * G independent FP64 chains.
+#pragma unroll
+    for (int g0 = 0; g0 < kPairs; g0 += G) {
+        T t0[G], t1[G], t2[G], t3[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const C x = a[base[g0 + g]], y = a[base[g0 + g] | (1 << B)];
+            t0[g] = m01.x * y.x;
+            t1[g] = m01.x * y.y;
+            t2[g] = m10.x * x.x;
+            t3[g] = m10.x * x.y;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const C y = a[base[g0 + g] | (1 << B)];
+            t0[g] = fma(-m01.y, y.y, t0[g]);
+            t1[g] = fma(m01.y, y.x, t1[g]);
+        }
         if (!REAL10) {
-            t2 = fma(-m10.y, x.y, t2);
-            t3 = fma(m10.y, x.x, t3);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const C x = a[base[g0 + g]];
+                t2[g] = fma(-m10.y, x.y, t2[g]);
+                t3[g] = fma(m10.y, x.x, t3[g]);
+            }
         }
         if (!REAL00) {
-            t0 = fma(-m00.y, x.y, t0);
-            t1 = fma(m00.y, x.x, t1);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const C x = a[base[g0 + g]];
+                t0[g] = fma(-m00.y, x.y, t0[g]);
+                t1[g] = fma(m00.y, x.x, t1[g]);
+            }
         }
-        t2 = fma(-m11.y, y.y, t2);
-        t3 = fma(m11.y, y.x, t3);
-        a[j].x = fma(m00.x, x.x, t0);
-        a[j].y = fma(m00.x, x.y, t1);
-        a[j | (1 << B)].x = fma(m11.x, y.x, t2);
-        a[j | (1 << B)].y = fma(m11.x, y.y, t3);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const C y = a[base[g0 + g] | (1 << B)];
+            t2[g] = fma(-m11.y, y.y, t2[g]);
+            t3[g] = fma(m11.y, y.x, t3[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int j = base[g0 + g];
+            const C x = a[j], y = a[j | (1 << B)];
+            a[j].x = fma(m00.x, x.x, t0[g]);
+            a[j].y = fma(m00.x, x.y, t1[g]);
+            a[j | (1 << B)].x = fma(m11.x, y.x, t2[g]);
+            a[j | (1 << B)].y = fma(m11.x, y.y, t3[g]);
+        }
     }
 }
 
@@ -297,7 +344,7 @@ __device__ __forceinline__ void apply_op(uint32_t word, uint32_t e_thr, typename
 }
 
 template <typename T, int R, int K, typename Idx>
-__global__ void __launch_bounds__(1 << (K - R), (K <= 11 ? 4 : 2))
+__global__ void __launch_bounds__(1 << (K - R), (K <= 11 ? QB_SWEEP_CTAS : 2))
 sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation, int m_log2) {
     using C = typename Cx<T>::type;
     constexpr int kTileSize = 1 << K;

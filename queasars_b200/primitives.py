@@ -221,9 +221,10 @@ class _B200Primitive:
             hit = self._ham_cache.get(key)
             if hit is not None and hit[0] is operator and hit[2] == fp:
                 return hit[1]
-        handle = self.engines[slot].hamiltonian(operator, build_table=build_table)
+        engines = self.engines  # (takes the lock itself: not inside the block below)
+        handle = engines[slot].hamiltonian(operator, build_table=build_table)
         with self._lock:
-            if len(self._ham_cache) > 64 * len(self.engines):
+            if len(self._ham_cache) > 64 * len(engines):
                 self._ham_cache.clear()
             self._ham_cache[key] = (operator, handle, fp)
         return handle
