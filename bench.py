@@ -466,8 +466,9 @@ def gate_apply_probe(engine, peak):
     from queasars_b200.circuit import QuantumCircuit
 
     def measure(gates, params, reps):
-        plan = engine.compile(gates)
-        _, _, _, (sweeps, _, _, _, _) = eng_mod.encoded_plan(gates, engine.tile_bits, engine.reg_bits, True)
+        # planned like the evaluators plan for a diagonal observable / sampling (engine.rewritten: trailing phases deferred)
+        plan = engine.compile(gates, drop_final_phases=True)
+        _, _, _, (sweeps, _, _, _, _) = eng_mod.encoded_plan(eng_mod.rewritten(gates, True), engine.tile_bits, engine.reg_bits, True)
         rb = engine.resident_batch([plan], None)
         rb.set_params([params])
         for _ in range(2):
@@ -598,7 +599,13 @@ def c4_probe(device):
     uniforms = np.random.default_rng(seed).random(shots)
     want = c_oracle.sample_indices(state, n, uniforms)
     got = sampler.sample_indices([circuits[0]], [params[0]], shots)[0]
-    out["index_mismatches_vs_c_oracle"] = int(np.count_nonzero(got != want))
+    flips = np.nonzero(got != want)[0]
+    probs = state.real**2 + state.imag**2
+    out["index_mismatches_vs_c_oracle"] = int(flips.size)
+    # a mismatch is a uniform within rounding of a CDF boundary (the GPU sums |psi|^2 in chunks, the oracle sequentially): it may
+    # only move the draw to the neighbouring state of non-zero probability
+    out["mismatches_are_neighbour_flips"] = bool(all(
+        probs[got[i]] > 0 and not np.any(probs[min(int(got[i]), int(want[i])) + 1 : max(int(got[i]), int(want[i]))] > 0) for i in flips))
     out["shots_checked"] = shots
     return out
 

@@ -205,6 +205,7 @@ class QuantumCircuit:
         self.data: list[CircuitInstruction] = []
         self.global_phase = 0.0
         self.num_clbits = 0
+        self._b200_version = 0  # bumped by every in-place change that keeps len(data) (plan-cache fingerprint, primitives.py)
 
     # ------------------------------------------------------------------ inspection
     def find_bit(self, bit: Qubit) -> _BitLocation:
@@ -438,6 +439,7 @@ class QuantumCircuit:
         bound = self._substitute(binding)
         if inplace:
             self.data = bound.data
+            self._b200_version += 1
             return None
         return bound
 

@@ -127,6 +127,37 @@ __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], c
     constexpr int kPairs = (CB >= 0) ? kNReg / 4 : kNReg / 2;
     constexpr int G = (QB_DENSE_GROUP < kPairs) ? QB_DENSE_GROUP : kPairs;
     using C = typename Cx<T>::type;
+#if QB_DENSE_GROUP == 1
+    // Term order chosen so that the last FMA of each output reads exactly the register it overwrites: the update is in place
+    // with four temporaries and no register moves at loop / switch merge points.
+#pragma unroll
+    for (int j = 0; j < kNReg; ++j) {
+        if (j & (1 << B)) continue;
+        if (CB >= 0 && !(j & (1 << (CB >= 0 ? CB : 0)))) continue;
+        const C x = a[j], y = a[j | (1 << B)];
+        T t0 = m01.x * y.x;
+        T t1 = m01.x * y.y;
+        T t2 = m10.x * x.x;
+        T t3 = m10.x * x.y;
+        t0 = fma(-m01.y, y.y, t0);
+        t1 = fma(m01.y, y.x, t1);
+        if (!REAL10) {
+            t2 = fma(-m10.y, x.y, t2);
+            t3 = fma(m10.y, x.x, t3);
+        }
+        if (!REAL00) {
+            t0 = fma(-m00.y, x.y, t0);
+            t1 = fma(m00.y, x.x, t1);
+        }
+        t2 = fma(-m11.y, y.y, t2);
+        t3 = fma(m11.y, y.x, t3);
+        a[j].x = fma(m00.x, x.x, t0);
+        a[j].y = fma(m00.x, x.y, t1);
+        a[j | (1 << B)].x = fma(m11.x, y.x, t2);
+        a[j | (1 << B)].y = fma(m11.x, y.y, t3);
+    }
+    return;
+#endif
     // compile-time list of the pair bases this gate touches (register index with bit B clear, and bit CB set when controlled)
     int base[kPairs];
     {

@@ -48,7 +48,10 @@ def _circuit_fingerprint(circuit) -> tuple:
     re-transpiles on every call: transpiling_primitives.py:47, 73-80): instruction count and parameter count.  A circuit
     whose fingerprint changed is re-parsed and re-compiled."""
     try:
-        return (len(circuit.data), int(circuit.num_parameters) if hasattr(circuit, "num_parameters") else len(circuit.parameters))
+        version = getattr(circuit, "_b200_version", None)  # the stand-in circuit class counts its mutations (O(1))
+        if version is not None:
+            return (len(circuit.data), version)
+        return (len(circuit.data), int(circuit.num_parameters))  # Qiskit: both O(1)
     except Exception:
         return ()
 

@@ -17,6 +17,8 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--runs", type=int, default=3)
 ap.add_argument("--dtype", default="complex128")
 ap.add_argument("--oploop", type=int, default=0, help="op-loop probe: u on every qubit (absorbed), then this many layers of u on the 4 highest qubits (one pass)")
+ap.add_argument("--hbm-regime", type=int, default=0, help="the bench's hbm_regime circuit: u on every qubit (absorbed into the product start), then 3 layers of 7 u gates on non-low qubits")
+ap.add_argument("--keep-phases", type=int, default=0, help="1: plans keep the final phases (statevector semantics); default: probabilities only, like the evaluators with a diagonal Hamiltonian")
 ap.add_argument("--simple", type=int, default=0, help="instead of an EVQE genome: this many u gates on distinct high qubits, repeated --layers times")
 args = ap.parse_args()
 
@@ -33,6 +35,18 @@ if args.oploop:
             circ.u(0.3 + g, 0.2 * layer, 0.1, args.n - 1 - g)
     plans = [engine.compile(gl.from_circuit(circ))] * args.batch
     params = [[] for _ in range(args.batch)]
+elif args.hbm_regime:
+    from queasars_b200.circuit import QuantumCircuit
+
+    n = args.n
+    circ = QuantumCircuit(n)
+    for q in range(n):
+        circ.u(0.1 + 0.01 * q, 0.2, 0.3, q)
+    for layer in range(3):
+        for g in range(7):
+            circ.u(0.3 + g, 0.2 * layer, 0.1, 4 + ((g * 3 + 7 * layer) % (n - 4)))
+    plans = [engine.compile(gl.from_circuit(circ), drop_final_phases=not args.keep_phases)] * args.batch
+    params = [[] for _ in range(args.batch)]
 elif args.simple:
     from queasars_b200.circuit import QuantumCircuit
 
@@ -43,7 +57,7 @@ elif args.simple:
     plans = [engine.compile(gl.from_circuit(circ))] * args.batch
     params = [[] for _ in range(args.batch)]
 else:
-    plans = [engine.compile(gl.from_evqe_individual(i)) for i in inds]
+    plans = [engine.compile(gl.from_evqe_individual(i), drop_final_phases=not args.keep_phases) for i in inds]
     params = [list(i.parameter_values) for i in inds]
 ham = engine.hamiltonian(gn.ising_operator(args.n)) if args.n <= 26 else None
 rb = engine.resident_batch(plans, ham)
