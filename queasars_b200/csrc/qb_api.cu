@@ -153,6 +153,9 @@ struct qb_context {
     uint64_t default_workspace = uint64_t(8) << 30;  // 80 % of the memory free at creation (cudaMemGetInfo is slow: ask once)
     int64_t launches = 0;
     int64_t next_id = 1;
+    int sweep_streams = 1;  // QB_SWEEP_STREAMS: groups of circuits whose sweep launches run on separate streams (tail overlap)
+    cudaStream_t aux_streams[8] = {};
+    cudaEvent_t fork_event = nullptr, join_events[8] = {};
     bool force_idx64 = false;  // qb_context_set_index_width(64): run the 64-bit-index sweep kernels at any size (tests)
     int tiles_log2 = -1;  // tiles per sweep CTA (log2); -1 = by size (4 tiles, 8 from 2^13 tiles per state on); QB_TILES_LOG2 overrides
     std::mutex mu;
@@ -362,7 +365,32 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
     return QB_OK;
 }
 
+// Sweep launches of one batch.  A sweep launch is a full drain point: the next sweep of ANY circuit waits for the slowest CTA of
+// this one.  With `sweep_streams` > 1 the (sorted) batch is cut into that many contiguous groups of circuits, each group runs its
+// own sweeps back to back on its own stream, so the tail of one group's launch overlaps the next launch of another group
+// (circuits are independent: no ordering between groups is needed).  Event-timed runs keep the single stream.
 template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
+    const int groups = events ? 1 : std::min<int>(ctx->sweep_streams, b.batch / 4);
+    if (groups > 1) {
+        QB_CUDA(cudaEventRecord(ctx->fork_event, ctx->stream));  // bind_kernel (and uploads) done before any group starts
+        const int fuse = b.fuse_expect ? (b.skip_final_store ? 2 : 1) : 0;
+        for (int g = 0; g < groups; ++g) {
+            const int lo = int(int64_t(b.batch) * g / groups), hi = int(int64_t(b.batch) * (g + 1) / groups);
+            cudaStream_t st = ctx->aux_streams[g];
+            QB_CUDA(cudaStreamWaitEvent(st, ctx->fork_event, 0));
+            for (int s = 0; s < b.max_sweeps; ++s) {
+                const int active = std::min(b.active[s], hi) - lo;  // entries are sorted by descending sweep count
+                if (active <= 0) break;
+                dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(active));
+                qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), qb::sweep_smem_bytes<T, R, K>(), st>>>(
+                    b.entries.as<qb::BatchEntry>() + lo, s, b.n_eff, fuse, b.tiles_log2);
+                QB_TRY(check_launch(ctx, "sweep_kernel"));
+            }
+            QB_CUDA(cudaEventRecord(ctx->join_events[g], st));
+            QB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->join_events[g], 0));
+        }
+        return QB_OK;
+    }
     for (int s = 0; s < b.max_sweeps; ++s) {
         // every CTA stages its circuit's sweep program once and walks 2^tiles_log2 consecutive tiles with it
         dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(b.active[s]));
@@ -593,6 +621,12 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     QB_CONFIGURE(3, 11)
 #undef QB_CONFIGURE
     if (const char* e = std::getenv("QB_TILES_LOG2")) ctx->tiles_log2 = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("QB_SWEEP_STREAMS")) ctx->sweep_streams = std::min(8, std::max(1, std::atoi(e)));
+    QB_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) {
+        QB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_streams[i], cudaStreamNonBlocking));
+        QB_CUDA(cudaEventCreateWithFlags(&ctx->join_events[i], cudaEventDisableTiming));
+    }
     *out = ctx.release();
     return QB_OK;
 }
@@ -607,6 +641,11 @@ int qb_context_destroy(qb_context* ctx) {
     ctx->pin_in.release(), ctx->pin_out.release(), ctx->scratch.release();
     if (ctx->pin_in_done) cudaEventDestroy(ctx->pin_in_done);
     if (ctx->pin_entries_done) cudaEventDestroy(ctx->pin_entries_done);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    for (int i = 0; i < 8; ++i) {
+        if (ctx->join_events[i]) cudaEventDestroy(ctx->join_events[i]);
+        if (ctx->aux_streams[i]) cudaStreamDestroy(ctx->aux_streams[i]);
+    }
     ctx->pin_entries.release();
     ctx->pin_res.release();
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);

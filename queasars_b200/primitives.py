@@ -217,9 +217,9 @@ class _B200Primitive:
                 self._pool_obj = ThreadPoolExecutor(max_workers=len(engines), thread_name_prefix="qb-device")
             return self._pool_obj
 
-    def hamiltonian_for(self, operator, build_table=None, slot: int = 0) -> HamiltonianHandle:
+    def hamiltonian_for(self, operator, build_table=None, slot: int = 0, fingerprint=None) -> HamiltonianHandle:
         key = (id(operator), build_table, slot)
-        fp = _operator_fingerprint(operator)
+        fp = _operator_fingerprint(operator) if fingerprint is None else fingerprint
         with self._lock:
             hit = self._ham_cache.get(key)
             if hit is not None and hit[0] is operator and hit[2] == fp:
@@ -411,9 +411,10 @@ class B200EstimatorV2(_B200Primitive):
             raise ValueError(f"{len(circuits)} circuits but {len(parameter_values)} parameter vectors")
         if not circuits:
             return np.zeros(0)
+        fp = _operator_fingerprint(operator)  # once per call: guards the cached device Hamiltonian against in-place edits
         if not self._needs_sharding(int(operator.num_qubits)):
-            self.hamiltonian_for(operator)  # validates the operator (and builds its device form) before anything is queued
-        return np.asarray(self._submit(("exp", id(operator), _operator_fingerprint(operator)), (operator, circuits, parameter_values)))
+            self.hamiltonian_for(operator, fingerprint=fp)  # validates the operator (and builds its device form) before anything is queued
+        return np.asarray(self._submit(("exp", id(operator), fp), (operator, circuits, parameter_values)))
 
     def _execute(self, key, payloads):
         operator = payloads[0][0]
@@ -436,9 +437,10 @@ class B200EstimatorV2(_B200Primitive):
                 out.append(np.asarray(flat[pos : pos + n], dtype=np.float64))
                 pos += n
             return out
-        resolved = self._resolve_all(circuits, values, probabilities_only=self.hamiltonian_for(operator).diagonal)
+        fp = key[2]
+        resolved = self._resolve_all(circuits, values, probabilities_only=self.hamiltonian_for(operator, fingerprint=fp).diagonal)
         flat = self._run_per_device(
-            resolved, lambda slot, plans, params: self.engines[slot].expectation(plans, params, self.hamiltonian_for(operator, slot=slot))
+            resolved, lambda slot, plans, params: self.engines[slot].expectation(plans, params, self.hamiltonian_for(operator, slot=slot, fingerprint=fp))
         )
         out, pos = [], 0
         for n in sizes:
