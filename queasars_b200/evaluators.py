@@ -97,6 +97,8 @@ class _WithInitialState:
         init_fp = _circuit_fingerprint(self._initial_state_circuit)
         out = []
         for circ in circuits:
+            if hasattr(circ, "layers") and not hasattr(circ, "data"):  # a genome: compose needs its circuit form
+                circ = circ.to_circuit() if hasattr(circ, "to_circuit") else circ.get_parameterized_quantum_circuit()
             hit = cache.get(id(circ))
             fp = (_circuit_fingerprint(circ), init_fp)  # either circuit edited in place since: compose again
             if hit is None or hit[0] is not circ or hit[2] != fp:

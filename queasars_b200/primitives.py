@@ -43,10 +43,30 @@ def get_engine(device: int = 0, dtype: str = "complex128") -> Engine:
         return eng
 
 
+def _is_genome(obj) -> bool:
+    """An EVQE individual (the reference's ``EVQEIndividual`` or ``queasars_b200.genome.Individual``) handed in where a circuit
+    is expected: the direct genome -> gate-list front end skips the QuantumCircuit altogether."""
+    return hasattr(obj, "layers") and hasattr(obj, "parameter_values") and not hasattr(obj, "data")
+
+
+def _parse(circuit):
+    if _is_genome(circuit):
+        from .gate_list import from_evqe_individual
+
+        return from_evqe_individual(circuit)
+    return from_circuit_or_none(circuit)
+
+
+def _width(circuit) -> int:
+    return int(circuit.n_qubits if _is_genome(circuit) else circuit.num_qubits)
+
+
 def _circuit_fingerprint(circuit) -> tuple:
     """Cheap guard against in-place edits of a circuit between two evaluations (Qiskit circuits are mutable; the reference
     re-transpiles on every call: transpiling_primitives.py:47, 73-80): instruction count and parameter count.  A circuit
     whose fingerprint changed is re-parsed and re-compiled."""
+    if _is_genome(circuit):
+        return (len(circuit.layers),)  # genomes are immutable value objects
     try:
         version = getattr(circuit, "_b200_version", None)  # the stand-in circuit class counts its mutations (O(1))
         if version is not None:
@@ -82,7 +102,7 @@ class _CircuitCache:
             hit = self._by_id.get(key)
             if hit is not None and hit["ref"]() is circuit and hit["fp"] == fp:
                 return hit
-        entry = {"ref": None, "fp": fp, "gates": from_circuit_or_none(circuit), "plans": {}, "home": None}
+        entry = {"ref": None, "fp": fp, "gates": _parse(circuit), "plans": {}, "home": None}
         try:
             entry["ref"] = weakref.ref(circuit, lambda _r, k=key: self._by_id.pop(k, None))
         except TypeError:  # not weak-referenceable: do not cache by identity
@@ -518,7 +538,7 @@ class B200SamplerV2(_B200Primitive):
         if not circuits:
             return np.zeros((0, int(shots)), dtype=np.int64)
         # circuits of different widths must not be merged into one native batch: the width is part of the coalescing key
-        widths = {int(c.num_qubits) for c in circuits}
+        widths = {_width(c) for c in circuits}
         if len(widths) != 1:
             raise ValueError("all circuits of one sampler submission must act on the same number of qubits")
         return np.asarray(self._submit(("smp", int(shots), widths.pop()), (circuits, parameter_values)))

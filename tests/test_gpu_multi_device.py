@@ -114,3 +114,27 @@ def test_circuit_and_operator_edited_in_place_are_recompiled():
     table2 = oq.diagonal_table(n, oq.diag_terms_from_labels(terms2))
     third = ev.evaluate_circuits([circ], [[]])[0]
     assert rel_err(third, float(np.dot(np.abs(oq.statevector(instr, n)) ** 2, table2))) < 1e-10
+
+
+def test_individuals_in_place_of_circuits_on_the_gpu():
+    """Direct genome -> gate-list front end through the evaluator: same values as the circuit route, and
+    as the oracle on the circuit the reference builds from the genome (individual.py:288-322)."""
+    from queasars_b200 import B200EstimatorV2, B200OperatorCircuitEvaluator
+    from queasars_b200 import genome as gn
+
+    n = 12
+    terms = random_ising(n, 6)
+    op = SparsePauliOp.from_list(terms)
+    table = oq.diagonal_table(n, oq.diag_terms_from_labels(terms))
+    pop = gn.random_population(n, 4, 6, True, 3)
+    values = [list(i.parameter_values) for i in pop]
+    ev = B200OperatorCircuitEvaluator(B200EstimatorV2(device=0, coalesce=False), 0.0, op)
+    direct = ev.evaluate_circuits(pop, values)
+    circuits = [i.to_circuit() for i in pop]
+    np.testing.assert_allclose(direct, ev.evaluate_circuits(circuits, values), rtol=0, atol=1e-12)
+    for g, circ, vals in zip(direct, circuits, values):
+        instr = []
+        for inst in circ.data:
+            ps = tuple(p.name if hasattr(p, "name") else float(p) for p in inst.operation.params)
+            instr.append((inst.operation.name, tuple(q._index for q in inst.qubits), ps))
+        assert rel_err(g, float(np.dot(np.abs(oq.statevector(instr, n, vals)) ** 2, table))) < 1e-10

@@ -104,3 +104,22 @@ def test_sampler_evaluators_and_pub_contract_host_flow(fake_engines):
     est = pr.B200EstimatorV2(devices="all", seed=1)
     res = est.run(pubs=[(circ, op, values)], precision=0.0).result()
     assert abs(float(res[0].data.evs) - oq.estimator_expectation(oq.statevector(instr, n, values), terms)) < 1e-10
+
+
+@pytest.mark.timeout(120)
+def test_individuals_are_accepted_in_place_of_circuits(fake_engines):
+    """the evaluators take EVQE individuals directly (genome -> gate list, no QuantumCircuit) and give the
+    values of the circuit the reference would have built from them (individual.py:288-322)."""
+    from queasars_b200 import genome as gn
+    from queasars_b200.evaluators import B200OperatorCircuitEvaluator, B200OperatorSamplerCircuitEvaluator
+
+    n = 5
+    op = SparsePauliOp.from_list(terms_for(n))
+    pop = gn.random_population(n, 3, 4, True, 2)
+    values = [list(i.parameter_values) for i in pop]
+    ev = B200OperatorCircuitEvaluator(pr.B200EstimatorV2(), 0.0, op)
+    direct = ev.evaluate_circuits(pop, values)
+    via_circuit = ev.evaluate_circuits([i.to_circuit() for i in pop], values)
+    np.testing.assert_allclose(direct, via_circuit, atol=1e-12)
+    smp = B200OperatorSamplerCircuitEvaluator(pr.B200SamplerV2(seed=3), 200, op, alpha=0.5)
+    np.testing.assert_allclose(smp.evaluate_circuits(pop, values), smp.evaluate_circuits([i.to_circuit() for i in pop], values), atol=1e-12)
