@@ -11,15 +11,16 @@ from queasars_b200 import _build  # noqa: E402
 
 OUT = os.path.join(_build.CSRC, "variants")
 os.makedirs(OUT, exist_ok=True)
-variants = [(4, 1), (4, 2), (4, 4), (3, 1), (3, 2), (3, 4), (3, 8)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
-for ctas, group in variants:
-    path = os.path.join(OUT, f"lib_c{ctas}_g{group}.so")
+variants = [(4, 1, 0), (4, 1, 1)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+for ctas, group, prefetch in variants:
+    path = os.path.join(OUT, f"lib_c{ctas}_g{group}_p{prefetch}.so")
     nvcc = "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *_build.NVCC_FLAGS, "-Xptxas=-v", f"-DQB_SWEEP_CTAS={ctas}", f"-DQB_DENSE_GROUP={group}", "-I", os.path.join(_build.ROOT, "include"), "-o", path, *_build.SOURCES]
+    cmd = [nvcc, *_build.NVCC_FLAGS, "-Xptxas=-v", f"-DQB_SWEEP_CTAS={ctas}", f"-DQB_DENSE_GROUP={group}", f"-DQB_L2_PREFETCH={prefetch}", "-I", os.path.join(_build.ROOT, "include"), "-o", path,
+           *_build.SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode:
         print(proc.stderr[-2000:])
         raise SystemExit(1)
     text = proc.stderr
     m = re.search(r"sweep_kernelIdLi4ELi11EjE.*?\n.*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\nptxas info\s*: Used (\d+) registers", text, re.S)
-    print(f"ctas={ctas} group={group}: regs={m.group(4)} spill_st={m.group(2)} spill_ld={m.group(3)}  -> {path}")
+    print(f"ctas={ctas} group={group} prefetch={prefetch}: regs={m.group(4)} spill_st={m.group(2)} spill_ld={m.group(3)}  -> {path}")
