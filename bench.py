@@ -602,10 +602,12 @@ def c4_probe(device):
     flips = np.nonzero(got != want)[0]
     probs = state.real**2 + state.imag**2
     out["index_mismatches_vs_c_oracle"] = int(flips.size)
-    # a mismatch is a uniform within rounding of a CDF boundary (the GPU sums |psi|^2 in chunks, the oracle sequentially): it may
-    # only move the draw to the neighbouring state of non-zero probability
-    out["mismatches_are_neighbour_flips"] = bool(all(
-        probs[got[i]] > 0 and not np.any(probs[min(int(got[i]), int(want[i])) + 1 : max(int(got[i]), int(want[i]))] > 0) for i in flips))
+    # a mismatch is a uniform within rounding of a CDF boundary (the GPU sums |psi|^2 in 512-amplitude chunks, the oracle
+    # sequentially): the two draws must then be CDF neighbours -- the probability mass strictly between them is below the
+    # rounding of a 2^26-term sum
+    between = [float(np.sum(probs[min(int(got[i]), int(want[i])) + 1 : max(int(got[i]), int(want[i]))])) for i in flips]
+    out["max_probability_mass_between_mismatched_draws"] = max(between) if between else 0.0
+    out["mismatches_are_cdf_neighbours"] = bool(all(m < 1e-10 for m in between) and all(probs[got[i]] > 0 for i in flips))
     out["shots_checked"] = shots
     return out
 

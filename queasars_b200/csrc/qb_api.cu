@@ -153,7 +153,9 @@ struct qb_context {
     uint64_t default_workspace = uint64_t(8) << 30;  // 80 % of the memory free at creation (cudaMemGetInfo is slow: ask once)
     int64_t launches = 0;
     int64_t next_id = 1;
-    int sweep_streams = 1;  // QB_SWEEP_STREAMS: groups of circuits whose sweep launches run on separate streams (tail overlap)
+    int l2_prefetch = -1;   // QB_L2_PREFETCH: next-tile L2 prefetch in the sweep kernel (-1: from 27 qubits on)
+    int sweep_group = 0;    // QB_SWEEP_GROUP: circuits per group (0: batch / sweep_streams)
+    int sweep_streams = 2;  // QB_SWEEP_STREAMS: groups of circuits whose sweep launches run on separate streams (tail overlap)
     cudaStream_t aux_streams[8] = {};
     cudaEvent_t fork_event = nullptr, join_events[8] = {};
     bool force_idx64 = false;  // qb_context_set_index_width(64): run the 64-bit-index sweep kernels at any size (tests)
@@ -370,24 +372,32 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
 // own sweeps back to back on its own stream, so the tail of one group's launch overlaps the next launch of another group
 // (circuits are independent: no ordering between groups is needed).  Event-timed runs keep the single stream.
 template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
-    const int groups = events ? 1 : std::min<int>(ctx->sweep_streams, b.batch / 4);
-    if (groups > 1) {
+    const int flags = (ctx->l2_prefetch < 0 ? b.n_eff >= 27 : ctx->l2_prefetch > 0) ? qb::QB_SWEEP_L2_PREFETCH : 0;
+    const int streams = events ? 1 : std::min<int>(ctx->sweep_streams, b.batch / 4);
+    if (streams > 1) {
+        // circuits per group: by default the batch is cut into one group per stream; QB_SWEEP_GROUP = c makes groups of c circuits
+        // that the streams take turns on (stream i runs groups i, i + streams, ... one after the other, each group all its sweeps
+        // back to back) -- with small groups the states in flight stay L2-resident between their sweeps
+        const int per = ctx->sweep_group > 0 ? std::min(ctx->sweep_group, b.batch) : (b.batch + streams - 1) / streams;
+        const int groups = (b.batch + per - 1) / per;
         QB_CUDA(cudaEventRecord(ctx->fork_event, ctx->stream));  // bind_kernel (and uploads) done before any group starts
         const int fuse = b.fuse_expect ? (b.skip_final_store ? 2 : 1) : 0;
+        for (int i = 0; i < streams; ++i) QB_CUDA(cudaStreamWaitEvent(ctx->aux_streams[i], ctx->fork_event, 0));
         for (int g = 0; g < groups; ++g) {
-            const int lo = int(int64_t(b.batch) * g / groups), hi = int(int64_t(b.batch) * (g + 1) / groups);
-            cudaStream_t st = ctx->aux_streams[g];
-            QB_CUDA(cudaStreamWaitEvent(st, ctx->fork_event, 0));
+            const int lo = g * per, hi = std::min(b.batch, lo + per);
+            cudaStream_t st = ctx->aux_streams[g % streams];
             for (int s = 0; s < b.max_sweeps; ++s) {
                 const int active = std::min(b.active[s], hi) - lo;  // entries are sorted by descending sweep count
                 if (active <= 0) break;
                 dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(active));
                 qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), qb::sweep_smem_bytes<T, R, K>(), st>>>(
-                    b.entries.as<qb::BatchEntry>() + lo, s, b.n_eff, fuse, b.tiles_log2);
+                    b.entries.as<qb::BatchEntry>() + lo, s, b.n_eff, fuse, b.tiles_log2, flags);
                 QB_TRY(check_launch(ctx, "sweep_kernel"));
             }
-            QB_CUDA(cudaEventRecord(ctx->join_events[g], st));
-            QB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->join_events[g], 0));
+        }
+        for (int i = 0; i < streams; ++i) {
+            QB_CUDA(cudaEventRecord(ctx->join_events[i], ctx->aux_streams[i]));
+            QB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->join_events[i], 0));
         }
         return QB_OK;
     }
@@ -396,7 +406,7 @@ template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context
         dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(b.active[s]));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s], ctx->stream));
         qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), qb::sweep_smem_bytes<T, R, K>(), ctx->stream>>>(
-            b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? (b.skip_final_store ? 2 : 1) : 0, b.tiles_log2);
+            b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? (b.skip_final_store ? 2 : 1) : 0, b.tiles_log2, flags);
         QB_TRY(check_launch(ctx, "sweep_kernel"));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s + 1], ctx->stream));
     }
@@ -622,6 +632,8 @@ int qb_context_create(int device, void* stream, qb_context** out) {
 #undef QB_CONFIGURE
     if (const char* e = std::getenv("QB_TILES_LOG2")) ctx->tiles_log2 = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("QB_SWEEP_STREAMS")) ctx->sweep_streams = std::min(8, std::max(1, std::atoi(e)));
+    if (const char* e = std::getenv("QB_SWEEP_GROUP")) ctx->sweep_group = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("QB_L2_PREFETCH")) ctx->l2_prefetch = std::atoi(e) ? 1 : 0;
     QB_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     for (int i = 0; i < 8; ++i) {
         QB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_streams[i], cudaStreamNonBlocking));

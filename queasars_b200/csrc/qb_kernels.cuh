@@ -33,11 +33,12 @@ namespace qb {
 #ifndef QB_DENSE_GROUP
 #define QB_DENSE_GROUP 1
 #endif
-//   QB_L2_PREFETCH  1: while a CTA works on tile i it asks the L2 to fetch tile i + 1 from HBM (cp.async.bulk.prefetch.L2, one 256-byte
-//                   run per thread), so the next tile's register loads hit L2 instead of paying the HBM latency
-#ifndef QB_L2_PREFETCH
-#define QB_L2_PREFETCH 0
-#endif
+// Run-time launch flags of sweep_kernel
+//   QB_SWEEP_L2_PREFETCH  while a CTA works on tile i it asks the L2 to fetch tile i + 1 from HBM (cp.async.bulk.prefetch.L2, one
+//                         256-byte run per thread), so the next tile's register loads hit L2 instead of paying the HBM latency.
+//                         Measured: +2..4 % on HBM-bound sweeps of 28-30-qubit states, -2 % on batches of 20-qubit states: the
+//                         host sets it from 27 qubits on (QB_L2_PREFETCH=0/1 overrides).
+constexpr int QB_SWEEP_L2_PREFETCH = 1;
 
 constexpr int kMaxSweepOps = 96;
 constexpr int kMaxSweepPasses = 16;
@@ -381,7 +382,7 @@ __device__ __forceinline__ void apply_op(uint32_t word, uint32_t e_thr, typename
 
 template <typename T, int R, int K, typename Idx>
 __global__ void __launch_bounds__(1 << (K - R), (K <= 11 ? QB_SWEEP_CTAS : 2))
-sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation, int m_log2) {
+sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, int fuse_expectation, int m_log2, int flags) {
     using C = typename Cx<T>::type;
     constexpr int kTileSize = 1 << K;
     constexpr int kThreadBits = K - R;
@@ -495,12 +496,11 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
         gthr_first |= bit << s_sweep.tile_qubits[s_pass[0].thread_bits[b]];
         gthr_last |= bit << s_sweep.tile_qubits[s_pass[n_pass - 1].thread_bits[b]];
     }
-#if QB_L2_PREFETCH
     // run number tid scattered over the tile qubits above the QB_LOW_BITS contiguous ones: the 256-byte run this thread prefetches
     Idx pf_off = 0;
 #pragma unroll
     for (int b = 0; b < K - QB_LOW_BITS; ++b) pf_off |= Idx((uint32_t(tid) >> b) & 1u) << s_sweep.tile_qubits[QB_LOW_BITS + b];
-#endif
+    const bool l2_prefetch = (flags & QB_SWEEP_L2_PREFETCH) && !product_start && !zero_start && tid < (1 << (K - QB_LOW_BITS));
     // product-state start: factor contributed by this thread's own tile bits (constant over the CTA's tiles)
     C p_thread;
     p_thread.x = T(1), p_thread.y = T(0);
@@ -601,13 +601,11 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                 for (int j = 0; j < kNReg; ++j) a[j] = ld_state(src + ix[j]);
             }
         }
-#if QB_L2_PREFETCH
-        if (!product_start && !zero_start && it + 1 < n_iter && tid < (1 << (K - QB_LOW_BITS))) {
+        if (l2_prefetch && it + 1 < n_iter) {
             const uint64_t nb = ((base | tile_mask) + 1ull) & not_tile;
-            const C* pf = st + (Idx(nb) | pf_off);  // sweeps after the first read `st` (src only differs for sweep 0 with a prefix state)
+            const C* pf = src + (Idx(nb) | pf_off);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(int(sizeof(C) << QB_LOW_BITS)) : "memory");
         }
-#endif
         // publishes this tile's words; also orders the previous tile's shared-memory reads before this tile's writes
         __syncthreads();
 

@@ -15,7 +15,7 @@ variants = [(4, 1, 0), (4, 1, 1)] if len(sys.argv) < 2 else [tuple(int(v) for v 
 for ctas, group, prefetch in variants:
     path = os.path.join(OUT, f"lib_c{ctas}_g{group}_p{prefetch}.so")
     nvcc = "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *_build.NVCC_FLAGS, "-Xptxas=-v", f"-DQB_SWEEP_CTAS={ctas}", f"-DQB_DENSE_GROUP={group}", f"-DQB_L2_PREFETCH={prefetch}", "-I", os.path.join(_build.ROOT, "include"), "-o", path,
+    cmd = [nvcc, *_build.NVCC_FLAGS, "-Xptxas=-v", f"-DQB_SWEEP_CTAS={ctas}", f"-DQB_DENSE_GROUP={group}", "-I", os.path.join(_build.ROOT, "include"), "-o", path,
            *_build.SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode:
