@@ -44,7 +44,7 @@ class SparsePauliOp:
 
     def __init__(self, data, coeffs=None, *, num_qubits: int | None = None):
         if isinstance(data, SparsePauliOp):
-            self._n, self._x, self._z, self._c = data._n, list(data._x), list(data._z), list(data._c)
+            self._n, self._x, self._z, self._c = data._n, list(data._x), list(data._z), np.array(data._c, dtype=complex)
             return
         labels = [data] if isinstance(data, str) else list(data)
         if not labels and num_qubits is None:
@@ -58,9 +58,9 @@ class SparsePauliOp:
             self._x.append(x)
             self._z.append(z)
         if coeffs is None:
-            self._c = [1.0 + 0.0j] * len(labels)
+            self._c = np.ones(len(labels), dtype=complex)
         else:
-            self._c = [complex(c) for c in np.atleast_1d(coeffs)]
+            self._c = np.array([complex(c) for c in np.atleast_1d(coeffs)], dtype=complex)
             if len(self._c) != len(labels):
                 raise ValueError("coeffs length does not match the number of labels")
 
@@ -68,7 +68,9 @@ class SparsePauliOp:
     @classmethod
     def _raw(cls, n, xs, zs, cs):
         op = cls.__new__(cls)
-        op._n, op._x, op._z, op._c = n, list(xs), list(zs), [complex(c) for c in cs]
+        # coefficients live in ONE ndarray that ``coeffs`` hands out without copying (like qiskit's SparsePauliOp): in-place edits are
+        # visible to the primitives' operator fingerprint at the cost of hashing a few kilobytes
+        op._n, op._x, op._z, op._c = n, list(xs), list(zs), np.array([complex(c) for c in cs], dtype=complex)
         return op
 
     @classmethod
@@ -126,7 +128,7 @@ class SparsePauliOp:
     def __add__(self, other):
         if not self._check(other):
             return NotImplemented
-        return SparsePauliOp._raw(self._n, self._x + other._x, self._z + other._z, self._c + other._c)
+        return SparsePauliOp._raw(self._n, self._x + other._x, self._z + other._z, np.concatenate([self._c, other._c]))
 
     def __radd__(self, other):
         if other == 0:  # allows builtin sum()
