@@ -142,6 +142,21 @@ struct DeviceBatch {
     }
 };
 
+// One (plan, Hamiltonian) evaluation captured as a CUDA graph: parameter upload from a fixed pinned buffer, bind, sweeps,
+// expectation, result download into a fixed pinned buffer.  Replayed by the single-circuit calls of an optimizer loop
+// (mutation.py:63-75 re-submits ONE circuit with new parameter values), where launch latency, not the GPU, sets the pace.
+struct SingleGraph {
+    DeviceBatch batch;
+    HostBuf pin_params, pin_out;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t last_use = 0;
+    size_t state_bytes = 0;
+    ~SingleGraph() {
+        if (exec) cudaGraphExecDestroy(exec);
+        pin_params.release(), pin_out.release();
+    }
+};
+
 }  // namespace
 
 struct qb_context {
@@ -177,6 +192,11 @@ struct qb_context {
     HostBuf pin_res;
     std::vector<PendingChunk> pending;
     size_t pending_results = 0;
+    // single-evaluation graphs (qb_evaluate_expectation with batch == 1), least recently used evicted first
+    bool use_graphs = true;  // QB_GRAPHS=0 disables
+    std::map<std::pair<int64_t, int64_t>, std::unique_ptr<SingleGraph>> single_graphs;
+    size_t single_graph_bytes = 0;
+    uint64_t use_clock = 0;
 };
 
 namespace {
@@ -567,6 +587,86 @@ int batch_read(qb_context* ctx, DeviceBatch& b, double* out_values) {
     return QB_OK;
 }
 
+void drop_single_graphs(qb_context* ctx, int64_t plan_id, int64_t ham_id) {
+    for (auto it = ctx->single_graphs.begin(); it != ctx->single_graphs.end();) {
+        bool hit = (plan_id && it->first.first == plan_id) || (ham_id && it->first.second == ham_id);
+        if (!hit && plan_id) {  // a prefixed plan whose prefix goes away is rebuilt on next use as well
+            Plan* pl = find_plan(ctx, it->first.first);
+            hit = pl && pl->prefix_id == plan_id;
+        }
+        if (hit) {
+            ctx->single_graph_bytes -= it->second->state_bytes;
+            it = ctx->single_graphs.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
+// qb_evaluate_expectation with batch == 1 through a cached CUDA graph.  Returns QB_OK with *handled = false when the graph path
+// does not apply (disabled, state too large to keep resident per circuit).
+int evaluate_single_graph(qb_context* ctx, int64_t plan_id, Plan* pl, Ham* ham, int64_t ham_id, const double* params, int64_t n_params,
+                          double* out_value, bool* handled) {
+    *handled = false;
+    const size_t state_bytes = (size_t(1) << pl->n_eff) * amp_bytes(pl->dtype);
+    const size_t budget = std::min<size_t>(size_t(4) << 30, (ctx->workspace_limit ? ctx->workspace_limit : ctx->default_workspace) / 8);
+    if (!ctx->use_graphs || state_bytes > budget / 4) return QB_OK;
+    if (n_params != pl->n_params)
+        return fail(QB_ERR_INVALID, "entry 0: got " + std::to_string(n_params) + " parameter values, circuit has " + std::to_string(pl->n_params) + " parameters");
+    const auto key = std::make_pair(plan_id, ham_id);
+    auto it = ctx->single_graphs.find(key);
+    if (it == ctx->single_graphs.end()) {
+        while (!ctx->single_graphs.empty() && (ctx->single_graph_bytes + state_bytes > budget || ctx->single_graphs.size() >= 256)) {
+            auto victim = ctx->single_graphs.begin();
+            for (auto j = ctx->single_graphs.begin(); j != ctx->single_graphs.end(); ++j)
+                if (j->second->last_use < victim->second->last_use) victim = j;
+            QB_CUDA(cudaStreamSynchronize(ctx->stream));
+            ctx->single_graph_bytes -= victim->second->state_bytes;
+            ctx->single_graphs.erase(victim);
+        }
+        auto sg = std::make_unique<SingleGraph>();
+        sg->state_bytes = state_bytes;
+        QB_TRY(build_batch(ctx, sg->batch, 1, &plan_id, ham, nullptr, 1, 0));  // (also computes a cached prefix state, uncaptured)
+        QB_TRY(sg->pin_params.reserve(std::max<size_t>(sizeof(double) * size_t(pl->n_params), 16)));
+        QB_TRY(sg->pin_out.reserve(sizeof(double)));
+        QB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaGraph_t graph = nullptr;
+        QB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = QB_OK;
+        if (pl->n_params && cudaMemcpyAsync(sg->batch.params.p, sg->pin_params.p, sizeof(double) * size_t(pl->n_params), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+            rc = fail(QB_ERR_CUDA, "graph capture: parameter upload");
+        if (rc == QB_OK) rc = launch_circuits(ctx, sg->batch, nullptr);
+        if (rc == QB_OK) rc = launch_expectation(ctx, sg->batch);
+        if (rc == QB_OK && cudaMemcpyAsync(sg->pin_out.p, sg->batch.out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            rc = fail(QB_ERR_CUDA, "graph capture: result download");
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != QB_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ctx->use_graphs = false;  // capture is not available here: fall back to plain launches for good
+            return rc != QB_OK ? rc : QB_OK;
+        }
+        ce = cudaGraphInstantiate(&sg->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            ctx->use_graphs = false;
+            return QB_OK;
+        }
+        ctx->single_graph_bytes += state_bytes;
+        it = ctx->single_graphs.emplace(key, std::move(sg)).first;
+    }
+    SingleGraph& sg = *it->second;
+    sg.last_use = ++ctx->use_clock;
+    if (pl->n_params) std::memcpy(sg.pin_params.p, params, sizeof(double) * size_t(pl->n_params));
+    QB_CUDA(cudaGraphLaunch(sg.exec, ctx->stream));
+    ctx->launches += sg.batch.max_sweeps + 2;  // bind + sweeps + reduction(s), as counted for plain launches
+    QB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_value = *static_cast<const double*>(sg.pin_out.p);
+    *handled = true;
+    return QB_OK;
+}
+
 size_t max_batch_for(qb_context* ctx, const Plan* pl) {
     const size_t state_bytes = (size_t(1) << pl->n_eff) * amp_bytes(pl->dtype);
     const size_t limit = ctx->workspace_limit ? ctx->workspace_limit : ctx->default_workspace;
@@ -633,6 +733,7 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     if (const char* e = std::getenv("QB_TILES_LOG2")) ctx->tiles_log2 = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("QB_SWEEP_STREAMS")) ctx->sweep_streams = std::min(8, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("QB_SWEEP_GROUP")) ctx->sweep_group = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("QB_GRAPHS")) ctx->use_graphs = std::atoi(e) != 0;
     if (const char* e = std::getenv("QB_L2_PREFETCH")) ctx->l2_prefetch = std::atoi(e) ? 1 : 0;
     QB_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     for (int i = 0; i < 8; ++i) {
@@ -647,6 +748,7 @@ int qb_context_destroy(qb_context* ctx) {
     if (!ctx) return QB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->single_graphs.clear();
     ctx->batches.clear();
     ctx->plans.clear();
     ctx->hams.clear();
@@ -816,6 +918,7 @@ int qb_plan_destroy(qb_context* ctx, int64_t plan_id) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     set_device(ctx);
     cudaStreamSynchronize(ctx->stream);
+    drop_single_graphs(ctx, plan_id, 0);
     return ctx->plans.erase(plan_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown plan id");
 }
 
@@ -963,6 +1066,7 @@ int qb_hamiltonian_destroy(qb_context* ctx, int64_t ham_id) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     set_device(ctx);
     cudaStreamSynchronize(ctx->stream);
+    drop_single_graphs(ctx, 0, ham_id);
     return ctx->hams.erase(ham_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
 }
 
@@ -1103,6 +1207,11 @@ int qb_evaluate_expectation(qb_context* ctx, int batch, const int64_t* plan_ids,
     if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
     Plan* first = find_plan(ctx, plan_ids[0]);
     if (!first) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[0]));
+    if (batch == 1) {  // the optimizer loop's call: replay the evaluation's CUDA graph
+        bool handled = false;
+        QB_TRY(evaluate_single_graph(ctx, plan_ids[0], first, ham, ham_id, params + param_offsets[0], param_offsets[1] - param_offsets[0], out_values, &handled));
+        if (handled) return QB_OK;
+    }
     const int chunk = int(std::min<size_t>(size_t(batch), max_batch_for(ctx, first)));
     for (int lo = 0; lo < batch; lo += chunk) {
         const int n = std::min(chunk, batch - lo);

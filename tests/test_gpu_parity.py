@@ -578,3 +578,30 @@ def test_term_counts_beyond_the_shared_memory_staging(engine):
         assert rel_err(got[0], want_diag) < 1e-10 and got[0] == got[1]
     want_full = oq.estimator_expectation(state, op_full.to_list())
     assert rel_err(engine.expectation([plan], [values], engine.hamiltonian(op_full))[0], want_full) < 1e-10
+
+
+def test_single_circuit_calls_replay_a_cuda_graph(engine):
+    """Batch-1 calls (the optimizer loop: mutation.py:63-75) go through a cached CUDA graph per (plan, Hamiltonian): same values
+    as the batched path for changing parameter values, for prefixed plans, and after the plan / Hamiltonian are destroyed and
+    rebuilt (the cached graph must go with them)."""
+    import gc
+
+    n = 13
+    terms = random_ising(n, 21)
+    rng = np.random.default_rng(8)
+    for lid in (None, -1):
+        instr, values, circ = evqe_case(n, 4, 77, None if lid is None else {lid})
+        gates = gl.from_circuit(circ)
+        for round_ in range(2):  # second round: new plan + Hamiltonian objects after the first ones were released
+            ham = engine.hamiltonian(SparsePauliOp.from_list(terms))
+            plan = engine.compile_with_prefix_reuse(gates, drop_final_phases=True) if lid is not None else engine.compile(gates, cache=False)
+            rows = [list(rng.uniform(0, 2 * math.pi, len(values))) for _ in range(6)]
+            single = [engine.expectation([plan], [r], ham)[0] for r in rows]
+            batched = engine.expectation([plan] * 6, rows, ham)
+            np.testing.assert_allclose(single, batched, rtol=0, atol=1e-12)
+            table = oq.diagonal_table(n, oq.diag_terms_from_labels(terms))
+            assert rel_err(single[0], float(np.dot(np.abs(oq.statevector(instr, n, rows[0])) ** 2, table))) < 1e-10
+            with pytest.raises(Exception):
+                engine.expectation([plan], [rows[0][:-1]], ham)
+            del plan, ham
+            gc.collect()

@@ -19,7 +19,8 @@ ind = gn.Individual.random(n, layers, True, 3)
 gates = gl.from_evqe_individual(ind, {-1})
 rng = np.random.default_rng(0)
 out = {"n_qubits": n, "layers": layers, "ops_total": len(gates.ops)}
-for name, plan in (("full_circuit", eng.compile(gates)), ("prefix_reuse", eng.compile_with_prefix_reuse(gates))):
+# plans as the evaluators compile them for a diagonal Hamiltonian (trailing phases deferred and dropped)
+for name, plan in (("full_circuit", eng.compile(gates, drop_final_phases=True)), ("prefix_reuse", eng.compile_with_prefix_reuse(gates, drop_final_phases=True))):
     for batch in (1, 2, 8):
         params = [list(rng.uniform(0, 6.28, gates.n_params)) for _ in range(batch)]
         for _ in range(20):
