@@ -283,7 +283,10 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+
+        # a rank that fails inside a collective section must not keep the others waiting for NCCL's default ten minutes
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
 
     from queasars_b200 import B200EstimatorV2, B200OperatorCircuitEvaluator
     from queasars_b200 import genome as gn
@@ -434,6 +437,7 @@ def run_b200(args):
             line["strong"] = guarded(lambda: strong_probe(dist, rank, world, engine, plans, ham, params, values, args, barrier, max_over_ranks))
             batch.close()
             line["api_all_devices"] = guarded(lambda: all_devices_probe(dist, rank, world, operator, circuits, params, values, args))
+            torch.cuda.set_device(local_rank)
             line["sharded"] = guarded(lambda: sharded_probe(dist, rank, world, local_rank))
     if world > 1:
         dist.destroy_process_group()
@@ -695,28 +699,40 @@ def all_devices_probe(dist, rank, world, operator, circuits, params, values, arg
     primitive: evqe.py:232-236).  Rank 0 runs it while the other ranks wait at a barrier with idle GPUs."""
     import torch
 
+    # the other ranks must wait on the CPU: an NCCL barrier is a kernel spinning on their GPU, i.e. on the GPUs rank 0 is about to use
+    cpu_group = dist.new_group(backend="gloo")
     torch.cuda.synchronize()
     dist.barrier()
-    out = None
+    torch.cuda.synchronize()
+    out, error = None, None
     if rank == 0:
-        from queasars_b200 import B200EstimatorV2, B200OperatorCircuitEvaluator
-
-        est = B200EstimatorV2(devices="all", dtype="complex128", coalesce=False)
-        ev = B200OperatorCircuitEvaluator(est, 0.0, operator)
-        for _ in range(3):
-            got = ev.evaluate_circuits(circuits, params)
-        assert np.allclose(got, values, rtol=0, atol=1e-12)
-        before = [e.launch_count for e in est.engines]
-        steps = max(10, args.steps)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            got = ev.evaluate_circuits(circuits, params)
-        dt = time.perf_counter() - t0
-        used = [e.launch_count - b for e, b in zip(est.engines, before)]
-        out = {"value": POPULATION * steps / dt, "unit": UNIT, "ms_per_call": 1e3 * dt / steps, "devices": est.devices_used(),
-               "kernel_launches_per_device": used, "pattern": "one evaluate_circuits call of 32 circuits per step, one process, one worker thread per GPU"}
-    dist.barrier()
+        try:
+            out = _all_devices_rank0(operator, circuits, params, values, args)
+        except Exception as exc:  # noqa: BLE001 -- the waiting ranks must be released whatever happens here
+            error = exc
+    dist.barrier(group=cpu_group)  # gloo: the waiting ranks sleep on a socket, their GPUs stay idle
+    if error is not None:
+        raise error
     return out
+
+
+def _all_devices_rank0(operator, circuits, params, values, args):
+    from queasars_b200 import B200EstimatorV2, B200OperatorCircuitEvaluator
+
+    est = B200EstimatorV2(devices="all", dtype="complex128", coalesce=False)
+    ev = B200OperatorCircuitEvaluator(est, 0.0, operator)
+    for _ in range(3):
+        got = ev.evaluate_circuits(circuits, params)
+    assert np.allclose(got, values, rtol=0, atol=1e-12)
+    before = [e.launch_count for e in est.engines]
+    steps = max(10, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        got = ev.evaluate_circuits(circuits, params)
+    dt = time.perf_counter() - t0
+    used = [e.launch_count - b for e, b in zip(est.engines, before)]
+    return {"value": POPULATION * steps / dt, "unit": UNIT, "ms_per_call": 1e3 * dt / steps, "devices": est.devices_used(),
+            "kernel_launches_per_device": used, "pattern": "one evaluate_circuits call of 32 circuits per step, one process, one worker thread per GPU"}
 
 
 def sharded_probe(dist, rank, world, local_rank):

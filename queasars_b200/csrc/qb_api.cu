@@ -208,10 +208,26 @@ constexpr int kMaxStagedTerms = 2000;
 // diagonal terms per diag_table_kernel launch (16 B each in shared memory); longer lists build the table in several launches
 constexpr int kTableTermChunk = 3000;
 
-int set_device(qb_context* ctx) {
-    QB_CUDA(cudaSetDevice(ctx->device));
-    return QB_OK;
-}
+// Every entry point works on its context's device and gives the calling thread its previous current device back on return: a host
+// program that drives several engines from one thread, or shares the thread with torch (bench.py, sharded.py), must not find its
+// current device changed behind its back (torch then allocates, and runs NCCL collectives, on the wrong GPU).
+struct DeviceScope {
+    int prev = -1, dev;
+    cudaError_t err;
+    explicit DeviceScope(int device) : dev(device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceScope() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
+#define QB_ON_DEVICE(ctx)                                                                                   \
+    DeviceScope qb_scope_((ctx)->device);                                                                   \
+    if (qb_scope_.err != cudaSuccess) return fail(QB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(qb_scope_.err))
 
 template <typename K> int configure_kernel(K kernel, size_t smem) {
     QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -700,7 +716,8 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     int count = 0;
     QB_CUDA(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(QB_ERR_INVALID, "no CUDA device " + std::to_string(device));
-    QB_CUDA(cudaSetDevice(device));
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail(QB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(scope.err));
     cudaDeviceProp prop;
     QB_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
@@ -746,7 +763,7 @@ int qb_context_create(int device, void* stream, qb_context** out) {
 
 int qb_context_destroy(qb_context* ctx) {
     if (!ctx) return QB_OK;
-    cudaSetDevice(ctx->device);
+    DeviceScope scope(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->single_graphs.clear();
     ctx->batches.clear();
@@ -787,7 +804,7 @@ int qb_context_set_index_width(qb_context* ctx, int bits) {
 
 int qb_context_synchronize(qb_context* ctx) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     QB_CUDA(cudaStreamSynchronize(ctx->stream));
     return QB_OK;
 }
@@ -884,7 +901,7 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
     }
 
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     auto pl = std::make_unique<Plan>();
     pl->n_qubits = n_qubits, pl->n_eff = n_eff, pl->dtype = dtype, pl->tile_bits = tile_bits, pl->reg_bits = reg_bits, pl->n_params = n_params, pl->n_ops = n_ops, pl->n_sweeps = n_sweeps, pl->n_pass_ops = n_pass_ops;
     QB_TRY(upload(ctx, pl->sweeps, sweeps, sizeof(qb_sweep) * size_t(n_sweeps)));
@@ -916,7 +933,7 @@ int qb_plan_set_prefix(qb_context* ctx, int64_t plan_id, int64_t prefix_plan_id)
 int qb_plan_destroy(qb_context* ctx, int64_t plan_id) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    set_device(ctx);
+    QB_ON_DEVICE(ctx);
     cudaStreamSynchronize(ctx->stream);
     drop_single_graphs(ctx, plan_id, 0);
     return ctx->plans.erase(plan_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown plan id");
@@ -928,7 +945,7 @@ int qb_hamiltonian_create(qb_context* ctx, int n_qubits, int n_terms, const uint
     if (!ctx || !ham_id) return fail(QB_ERR_INVALID, "null argument");
     if (n_qubits < 1 || n_qubits > 40 || n_terms < 0) return fail(QB_ERR_INVALID, "bad Hamiltonian shape");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     auto ham = std::make_unique<Ham>();
     ham->n_qubits = n_qubits;
     // group by x mask, keeping first-appearance order; weights w = coeff * i^{#Y}
@@ -1064,7 +1081,7 @@ int qb_hamiltonian_create(qb_context* ctx, int n_qubits, int n_terms, const uint
 int qb_hamiltonian_destroy(qb_context* ctx, int64_t ham_id) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    set_device(ctx);
+    QB_ON_DEVICE(ctx);
     cudaStreamSynchronize(ctx->stream);
     drop_single_graphs(ctx, 0, ham_id);
     return ctx->hams.erase(ham_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
@@ -1074,7 +1091,7 @@ int qb_hamiltonian_diag_energies(qb_context* ctx, int64_t ham_id, int64_t n_stat
     if (!ctx || (n_states > 0 && (!states || !out_energies))) return fail(QB_ERR_INVALID, "null argument");
     if (n_states <= 0) return QB_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     Ham* ham = find_ham(ctx, ham_id);
     if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
     if (!ham->diagonal) return fail(QB_ERR_INVALID, "Hamiltonian has non-diagonal terms");
@@ -1101,7 +1118,7 @@ int qb_hamiltonian_diag_energies(qb_context* ctx, int64_t ham_id, int64_t n_stat
 int qb_batch_create(qb_context* ctx, int batch, const int64_t* plan_ids, int64_t ham_id, int64_t* batch_id) {
     if (!ctx || !plan_ids || !batch_id) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     Ham* ham = nullptr;
     if (ham_id) {
         ham = find_ham(ctx, ham_id);
@@ -1122,7 +1139,7 @@ static DeviceBatch* find_batch(qb_context* ctx, int64_t id) {
 int qb_batch_set_params(qb_context* ctx, int64_t batch_id, const double* params, const int64_t* param_offsets) {
     if (!ctx || !param_offsets) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     DeviceBatch* b = find_batch(ctx, batch_id);
     if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
     return batch_upload_params(ctx, *b, params, param_offsets);
@@ -1131,7 +1148,7 @@ int qb_batch_set_params(qb_context* ctx, int64_t batch_id, const double* params,
 int qb_batch_run(qb_context* ctx, int64_t batch_id) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     DeviceBatch* b = find_batch(ctx, batch_id);
     if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
     const int64_t before = ctx->launches;
@@ -1144,7 +1161,7 @@ int qb_batch_run(qb_context* ctx, int64_t batch_id) {
 int qb_batch_run_timed(qb_context* ctx, int64_t batch_id, int max_launches, float* sweep_ms, int32_t* sweep_states, int* n_launches) {
     if (!ctx || !sweep_ms || !sweep_states || !n_launches) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     DeviceBatch* b = find_batch(ctx, batch_id);
     if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
     if (max_launches < b->max_sweeps) return fail(QB_ERR_INVALID, "output arrays too small");
@@ -1169,7 +1186,7 @@ int qb_batch_run_timed(qb_context* ctx, int64_t batch_id, int max_launches, floa
 int qb_batch_read(qb_context* ctx, int64_t batch_id, double* out_values) {
     if (!ctx || !out_values) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     DeviceBatch* b = find_batch(ctx, batch_id);
     if (!b) return fail(QB_ERR_NOT_FOUND, "unknown batch id");
     return batch_read(ctx, *b, out_values);
@@ -1178,7 +1195,7 @@ int qb_batch_read(qb_context* ctx, int64_t batch_id, double* out_values) {
 int qb_batch_destroy(qb_context* ctx, int64_t batch_id) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    set_device(ctx);
+    QB_ON_DEVICE(ctx);
     cudaStreamSynchronize(ctx->stream);
     return ctx->batches.erase(batch_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown batch id");
 }
@@ -1202,7 +1219,7 @@ int qb_evaluate_expectation(qb_context* ctx, int batch, const int64_t* plan_ids,
     if (!ctx || !plan_ids || !param_offsets || !out_values) return fail(QB_ERR_INVALID, "null argument");
     if (batch <= 0) return QB_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     Ham* ham = find_ham(ctx, ham_id);
     if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
     Plan* first = find_plan(ctx, plan_ids[0]);
@@ -1230,7 +1247,7 @@ int qb_sample(qb_context* ctx, int batch, const int64_t* plan_ids, const double*
     if (!ctx || !plan_ids || !param_offsets || !uniforms || !out_indices) return fail(QB_ERR_INVALID, "null argument");
     if (batch <= 0 || shots <= 0) return QB_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     Plan* first = find_plan(ctx, plan_ids[0]);
     if (!first) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[0]));
     const int chunk = int(std::min<size_t>(size_t(batch), max_batch_for(ctx, first)));
@@ -1287,7 +1304,7 @@ int qb_sample(qb_context* ctx, int batch, const int64_t* plan_ids, const double*
 int qb_statevector(qb_context* ctx, int64_t plan_id, const double* params, int n_params, double* out_re_im) {
     if (!ctx || !out_re_im) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     Plan* pl = find_plan(ctx, plan_id);
     if (!pl) return fail(QB_ERR_NOT_FOUND, "unknown plan id");
     DeviceBatch& b = ctx->oneshot;
@@ -1314,7 +1331,7 @@ int qb_apply_plan_device(qb_context* ctx, int64_t plan_id, const double* params_
                          uint64_t index_offset) {
     if (!ctx || !d_state) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     DeviceBatch b;
     QB_TRY(build_batch(ctx, b, 1, &plan_id, nullptr, d_state, init_zero_state, index_offset));
     const int64_t offs[2] = {0, n_params};
@@ -1329,7 +1346,7 @@ int qb_expectation_device(qb_context* ctx, int64_t ham_id, int dtype, int n_loca
     if (!ctx || !d_state || !out_value) return fail(QB_ERR_INVALID, "null argument");
     if (n_local < 8 || n_local > 36) return fail(QB_ERR_INVALID, "n_local out of range");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     Ham* ham = find_ham(ctx, ham_id);
     if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
     const size_t n_part = std::max<size_t>(1024, n_local >= qb::kExpTileBits ? size_t(1) << (n_local - qb::kExpTileBits) : 0);
@@ -1349,7 +1366,7 @@ int qb_sample_device(qb_context* ctx, int dtype, int n_local, const void* d_stat
     if (n_local < qb::kChunkBits || n_local > 36) return fail(QB_ERR_INVALID, "n_local out of range");
     if (dtype != QB_C128 && dtype != QB_C64) return fail(QB_ERR_INVALID, "dtype must be QB_C128 or QB_C64");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     const uint64_t size = uint64_t(1) << n_local;
     const uint64_t n_chunks = size >> qb::kChunkBits;
     const size_t u_bytes = sizeof(double) * size_t(shots);
@@ -1400,7 +1417,7 @@ int qb_swap_global_p2p(qb_context* ctx, int dtype, int n_local, const void* d_st
     args.g = n_global, args.rank = rank;
     args.run_bits = std::min(qb::kSwapRunBits, n_local - n_global);
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     const uint64_t size = uint64_t(1) << n_local;
     const int blocks = int(std::min<uint64_t>(uint64_t(ctx->sm_count) * 8, std::max<uint64_t>(1, size / (256 * 4))));
     if (dtype == QB_C128) qb::swap_p2p_kernel<double2><<<blocks, 256, 0, ctx->stream>>>(static_cast<const double2*>(d_state), args, size);
@@ -1413,7 +1430,7 @@ int qb_evaluate_expectation_submit(qb_context* ctx, int batch, const int64_t* pl
     if (!ctx || !plan_ids || !param_offsets) return fail(QB_ERR_INVALID, "null argument");
     if (batch <= 0) return QB_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     Ham* ham = find_ham(ctx, ham_id);
     if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
     Plan* first = find_plan(ctx, plan_ids[0]);
@@ -1442,7 +1459,7 @@ int qb_evaluate_expectation_submit(qb_context* ctx, int batch, const int64_t* pl
 int qb_evaluate_expectation_collect(qb_context* ctx, int total, double* out_values) {
     if (!ctx || (total > 0 && !out_values)) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     const size_t have = ctx->pending_results;
     std::vector<qb_context::PendingChunk> chunks;
@@ -1464,7 +1481,7 @@ uint64_t qb_context_workspace(qb_context* ctx) { return ctx ? (ctx->workspace_li
 int qb_device_alloc(qb_context* ctx, uint64_t bytes, void** out_ptr) {
     if (!ctx || !out_ptr || !bytes) return fail(QB_ERR_INVALID, "null argument / zero size");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, size_t(bytes));
     if (e != cudaSuccess) {
@@ -1479,7 +1496,7 @@ int qb_device_free(qb_context* ctx, void* ptr) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     if (!ptr) return QB_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     QB_CUDA(cudaStreamSynchronize(ctx->stream));
     QB_CUDA(cudaFree(ptr));
     return QB_OK;
@@ -1488,7 +1505,7 @@ int qb_device_free(qb_context* ctx, void* ptr) {
 int qb_device_read(qb_context* ctx, const void* src, uint64_t offset, uint64_t bytes, void* host_out) {
     if (!ctx || !src || !host_out) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     QB_CUDA(cudaMemcpyAsync(host_out, static_cast<const unsigned char*>(src) + offset, size_t(bytes), cudaMemcpyDeviceToHost, ctx->stream));
     QB_CUDA(cudaStreamSynchronize(ctx->stream));
     return QB_OK;
@@ -1498,7 +1515,7 @@ int qb_enable_peer_access(qb_context* ctx, int peer_device) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     if (peer_device == ctx->device) return QB_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     int can = 0;
     QB_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
     if (!can) return fail(QB_ERR_CUDA, "device " + std::to_string(ctx->device) + " cannot map the memory of device " + std::to_string(peer_device) + " (no peer access)");
@@ -1516,7 +1533,7 @@ static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes")
 int qb_ipc_export(qb_context* ctx, void* ptr, unsigned char handle_out[64]) {
     if (!ctx || !ptr || !handle_out) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     cudaIpcMemHandle_t h;
     QB_CUDA(cudaIpcGetMemHandle(&h, ptr));
     std::memcpy(handle_out, &h, 64);
@@ -1526,7 +1543,7 @@ int qb_ipc_export(qb_context* ctx, void* ptr, unsigned char handle_out[64]) {
 int qb_ipc_open(qb_context* ctx, const unsigned char handle[64], void** out_ptr) {
     if (!ctx || !handle || !out_ptr) return fail(QB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle, 64);
     void* p = nullptr;
@@ -1539,7 +1556,7 @@ int qb_ipc_close(qb_context* ctx, void* mapped_ptr) {
     if (!ctx) return fail(QB_ERR_INVALID, "null context");
     if (!mapped_ptr) return QB_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    QB_TRY(set_device(ctx));
+    QB_ON_DEVICE(ctx);
     QB_CUDA(cudaIpcCloseMemHandle(mapped_ptr));
     return QB_OK;
 }

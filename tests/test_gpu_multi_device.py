@@ -138,3 +138,27 @@ def test_individuals_in_place_of_circuits_on_the_gpu():
             ps = tuple(p.name if hasattr(p, "name") else float(p) for p in inst.operation.params)
             instr.append((inst.operation.name, tuple(q._index for q in inst.qubits), ps))
         assert rel_err(g, float(np.dot(np.abs(oq.statevector(instr, n, vals)) ** 2, table))) < 1e-10
+
+
+def test_engine_calls_leave_the_callers_current_device_alone():
+    """A host thread that drives engines on several GPUs (or shares the thread with torch) must find its current CUDA device
+    unchanged after every native call: torch would otherwise allocate -- and run NCCL collectives -- on the wrong GPU."""
+    import torch
+
+    from queasars_b200 import _native
+    from queasars_b200.primitives import get_engine
+
+    n_dev = _native.device_count()
+    torch.cuda.set_device(0)
+    probe = torch.zeros(1, device="cuda")
+    last = get_engine(n_dev - 1)
+    instr, values, circ = evqe_case(12, 2, 5)
+    from queasars_b200 import gate_list as gl
+
+    plan = last.compile(gl.from_circuit(circ))
+    ham = last.hamiltonian(SparsePauliOp.from_list(random_ising(12, 2)))
+    last.expectation([plan], [values], ham)
+    last.expectation([plan] * 5, [values] * 5, ham)
+    last.statevector(plan, values)
+    assert torch.cuda.current_device() == 0
+    assert torch.zeros(1, device="cuda").device == probe.device
