@@ -34,8 +34,8 @@ namespace qb {
 #define QB_DENSE_GROUP 1
 #endif
 // Run-time launch flags of sweep_kernel
-//   QB_SWEEP_L2_PREFETCH  while a CTA works on tile i it asks the L2 to fetch tile i + 1 from HBM (cp.async.bulk.prefetch.L2, one
-//                         256-byte run per thread), so the next tile's register loads hit L2 instead of paying the HBM latency.
+//   QB_SWEEP_L2_PREFETCH  while a CTA works on tile i it asks the L2 to fetch tile i + 1 from HBM (prefetch.global.L2, one 256-byte
+//                         run per thread), so the next tile's register loads hit L2 instead of paying the HBM latency.
 //                         Measured: +2..4 % on HBM-bound sweeps of 28-30-qubit states, -2 % on batches of 20-qubit states: the
 //                         host sets it from 27 qubits on (QB_L2_PREFETCH=0/1 overrides).
 constexpr int QB_SWEEP_L2_PREFETCH = 1;
@@ -603,8 +603,11 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
         }
         if (l2_prefetch && it + 1 < n_iter) {
             const uint64_t nb = ((base | tile_mask) + 1ull) & not_tile;
-            const C* pf = src + (Idx(nb) | pf_off);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(int(sizeof(C) << QB_LOW_BITS)) : "memory");
+            // per-lane addresses: the bulk form (cp.async.bulk.prefetch.L2 -> UBLKPF) takes a warp-uniform address and would be
+            // issued lane by lane; two plain 128-byte line prefetches per 256-byte run cost two instructions per thread
+            const char* pf = reinterpret_cast<const char*>(src + (Idx(nb) | pf_off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            if (sizeof(C) == 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128));
         }
         // publishes this tile's words; also orders the previous tile's shared-memory reads before this tile's writes
         __syncthreads();
