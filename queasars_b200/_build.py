@@ -48,5 +48,22 @@ def build_native(force: bool = False, verbose: bool = False, defines: tuple = ()
     return out_path
 
 
+PYHELPER_SRC = os.path.join(CSRC, "qb_pyhelper.c")
+PYHELPER_PATH = os.path.join(CSRC, "libqb_pyhelper.so")
+
+
+def build_pyhelper(force: bool = False) -> str:
+    """The host-side list -> float64 marshalling helper (CPython C API; optional: the engine falls back to NumPy without it)."""
+    import sysconfig
+
+    if not force and os.path.exists(PYHELPER_PATH) and os.path.getmtime(PYHELPER_PATH) >= os.path.getmtime(PYHELPER_SRC):
+        return PYHELPER_PATH
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", PYHELPER_PATH, PYHELPER_SRC]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return PYHELPER_PATH
+
+
 if __name__ == "__main__":
     print(build_native(force=True, verbose=True))

@@ -132,3 +132,23 @@ def device_count() -> int:
     out = c_int()
     check(load().qb_device_count(ctypes.byref(out)))
     return int(out.value)
+
+
+_pyhelper = None
+
+
+def pyhelper():
+    """ctypes.PyDLL handle of the list -> float64 marshalling helper (csrc/qb_pyhelper.c), or False when it is not built /
+    not loadable (callers then convert with NumPy: this is host-side data marshalling, not a compute fallback)."""
+    global _pyhelper
+    if _pyhelper is None:
+        from ._build import PYHELPER_PATH
+
+        try:
+            lib = ctypes.PyDLL(PYHELPER_PATH)
+            lib.qb_pack_rows.argtypes = [ctypes.py_object, c_void_p, c_void_p, ctypes.c_longlong]
+            lib.qb_pack_rows.restype = ctypes.c_longlong
+            _pyhelper = lib
+        except OSError:
+            _pyhelper = False
+    return _pyhelper

@@ -1,0 +1,54 @@
+/* Host-side helper (CPython C API, loaded with ctypes.PyDLL): turns the reference's ``parameter_values: list[list[float]]``
+ * (/root/reference/queasars/circuit_evaluation/circuit_evaluation.py:62-87; built with ``ndarray.tolist()`` at
+ * evqe/evolutionary_algorithm/mutation.py:64) into the flat float64 buffer the C-ABI takes, in one pass and without one NumPy
+ * call per row.  Pure data marshalling: no arithmetic of the hot path lives here, and the engine works without it (NumPy path).
+ *
+ * Build: gcc -O2 -shared -fPIC -I<python include dir> -o libqb_pyhelper.so qb_pyhelper.c
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+
+/* rows: sequence of n_rows sequences of numbers; expected[i] = number of values row i must have; out: sum(expected) doubles.
+ * Returns the number of doubles written, -(i + 1) when row i has the wrong length, LLONG_MIN on a type error (Python exception
+ * cleared). */
+long long qb_pack_rows(PyObject* rows, double* out, const long long* expected, long long n_rows) {
+    PyObject* outer = PySequence_Fast(rows, "rows must be a sequence");
+    if (!outer) {
+        PyErr_Clear();
+        return LLONG_MIN;
+    }
+    if (PySequence_Fast_GET_SIZE(outer) != n_rows) {
+        Py_DECREF(outer);
+        return LLONG_MIN;
+    }
+    long long pos = 0;
+    for (long long i = 0; i < n_rows; ++i) {
+        PyObject* row = PySequence_Fast(PySequence_Fast_GET_ITEM(outer, i), "row must be a sequence");
+        if (!row) {
+            PyErr_Clear();
+            Py_DECREF(outer);
+            return LLONG_MIN;
+        }
+        const Py_ssize_t n = PySequence_Fast_GET_SIZE(row);
+        if ((long long)n != expected[i]) {
+            Py_DECREF(row);
+            Py_DECREF(outer);
+            return -(i + 1);
+        }
+        PyObject** items = PySequence_Fast_ITEMS(row);
+        for (Py_ssize_t j = 0; j < n; ++j) {
+            PyObject* v = items[j];
+            double d = PyFloat_CheckExact(v) ? PyFloat_AS_DOUBLE(v) : PyFloat_AsDouble(v);
+            if (d == -1.0 && PyErr_Occurred()) {
+                PyErr_Clear();
+                Py_DECREF(row);
+                Py_DECREF(outer);
+                return LLONG_MIN;
+            }
+            out[pos++] = d;
+        }
+        Py_DECREF(row);
+    }
+    Py_DECREF(outer);
+    return pos;
+}

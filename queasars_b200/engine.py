@@ -306,6 +306,19 @@ class Engine:
             offsets[1:] = np.arange(1, len(plans) + 1, dtype=np.int64) * width
             flat = np.ascontiguousarray(params).reshape(-1)
             return ids, (flat if flat.size else np.zeros(1, dtype=np.float64)), offsets
+        helper = _native.pyhelper() if isinstance(params, (list, tuple)) and params and isinstance(params[0], (list, tuple)) else None
+        if helper:
+            # the reference's list[list[float]]: one C pass over the Python objects instead of one NumPy call per row
+            expected = np.fromiter((p.n_params for p in plans), dtype=np.int64, count=len(plans))
+            np.cumsum(expected, out=offsets[1:])
+            flat = np.empty(max(1, int(offsets[-1])), dtype=np.float64)
+            got = helper.qb_pack_rows(params, _native.ptr(flat), _native.ptr(expected), len(plans))
+            if got == offsets[-1]:
+                return ids, flat, offsets
+            if -len(plans) <= got < 0:
+                i = int(-got - 1)
+                raise ValueError(f"circuit {i} has {plans[i].n_params} parameters but {len(params[i])} values were given")
+            offsets[:] = 0  # rows the helper cannot read (nested arrays, exotic number types): the NumPy path below decides
         chunks = []
         for i, (pl, vals) in enumerate(zip(plans, params)):
             arr = np.asarray(vals, dtype=np.float64).reshape(-1)
