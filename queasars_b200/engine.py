@@ -10,6 +10,7 @@ cross-thread coalescing on top.
 from __future__ import annotations
 
 import ctypes
+import functools
 import math
 import os
 import threading
@@ -121,6 +122,7 @@ def merge_duplicate_terms(x, z, c):
     return uniq[order, 0].copy(), uniq[order, 1].copy(), summed[order]
 
 
+@functools.lru_cache(maxsize=256)
 def pipeline_split_point(n: int, n_eff: int, tile_bits: int, sm_count: int) -> Optional[int]:
     """First-chunk size of the two-chunk pipelined submission of ``n`` evaluations of ``n_eff``-qubit states: the split (between
     a fifth and half of the list) that wastes the fewest partially filled waves of sweep CTAs -- a state contributes

@@ -98,10 +98,9 @@ class _CircuitCache:
     def _entry(self, circuit):
         key = id(circuit)
         fp = _circuit_fingerprint(circuit)
-        with self._lock:
-            hit = self._by_id.get(key)
-            if hit is not None and hit["ref"]() is circuit and hit["fp"] == fp:
-                return hit
+        hit = self._by_id.get(key)  # (dict.get is atomic under the GIL: the hot path takes no lock)
+        if hit is not None and hit["ref"]() is circuit and hit["fp"] == fp:
+            return hit
         entry = {"ref": None, "fp": fp, "gates": _parse(circuit), "plans": {}, "home": None}
         try:
             entry["ref"] = weakref.ref(circuit, lambda _r, k=key: self._by_id.pop(k, None))
