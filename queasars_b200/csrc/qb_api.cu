@@ -168,7 +168,7 @@ struct qb_context {
     uint64_t default_workspace = uint64_t(8) << 30;  // 80 % of the memory free at creation (cudaMemGetInfo is slow: ask once)
     int64_t launches = 0;
     int64_t next_id = 1;
-    int l2_prefetch = -1;   // QB_L2_PREFETCH: next-tile L2 prefetch in the sweep kernel (-1: from 27 qubits on)
+    int l2_prefetch = 1;    // QB_L2_PREFETCH=0 switches the next-tile L2 prefetch of the sweep kernel off
     int sweep_group = 0;    // QB_SWEEP_GROUP: circuits per group (0: batch / sweep_streams)
     int sweep_streams = 2;  // QB_SWEEP_STREAMS: groups of circuits whose sweep launches run on separate streams (tail overlap)
     cudaStream_t aux_streams[8] = {};
@@ -408,7 +408,7 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
 // own sweeps back to back on its own stream, so the tail of one group's launch overlaps the next launch of another group
 // (circuits are independent: no ordering between groups is needed).  Event-timed runs keep the single stream.
 template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
-    const int flags = (ctx->l2_prefetch < 0 ? b.n_eff >= 27 : ctx->l2_prefetch > 0) ? qb::QB_SWEEP_L2_PREFETCH : 0;
+    const int flags = ctx->l2_prefetch != 0 ? qb::QB_SWEEP_L2_PREFETCH : 0;
     const int streams = events ? 1 : std::min<int>(ctx->sweep_streams, b.batch / 4);
     if (streams > 1) {
         // circuits per group: by default the batch is cut into one group per stream; QB_SWEEP_GROUP = c makes groups of c circuits

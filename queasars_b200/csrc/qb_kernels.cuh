@@ -36,8 +36,9 @@ namespace qb {
 // Run-time launch flags of sweep_kernel
 //   QB_SWEEP_L2_PREFETCH  while a CTA works on tile i it asks the L2 to fetch tile i + 1 from HBM (prefetch.global.L2, one 256-byte
 //                         run per thread), so the next tile's register loads hit L2 instead of paying the HBM latency.
-//                         Measured: +2..4 % on HBM-bound sweeps of 28-30-qubit states, -2 % on batches of 20-qubit states: the
-//                         host sets it from 27 qubits on (QB_L2_PREFETCH=0/1 overrides).
+//                         Measured (per-lane line prefetches): +3..6 % on the read+write sweeps of 26-30-qubit states, neutral on
+//                         batches of 20-qubit states; on by default (QB_L2_PREFETCH=0 switches it off).  The bulk form
+//                         (cp.async.bulk.prefetch.L2 -> UBLKPF) takes a warp-uniform address and was issued lane by lane: -2 %.
 constexpr int QB_SWEEP_L2_PREFETCH = 1;
 
 constexpr int kMaxSweepOps = 96;

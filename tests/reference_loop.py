@@ -88,6 +88,31 @@ def jssp_4q(ref):
     return encoder, encoder.get_problem_hamiltonian()
 
 
+JSSP_INSTANCES = {
+    # name: (jobs as ((machine, duration), ...), makespan_limit, n_qubits, notebook convergence value = minimum diagonal energy)
+    "4q": (((("m0", 1), ("m1", 1)), (("m0", 1), ("m1", 1))), 3, 4, 63.5),  # evqe_jssp_small_examples.ipynb cells 4, 8, 14
+    "5q": (((("m0", 1), ("m1", 2)), (("m0", 1), ("m1", 1), ("m2", 1))), 4, 5, 61.6),  # same notebook, cells 23, 27, 33
+    "8q": (((("m0", 2), ("m1", 1)), (("m0", 1), ("m1", 2))), 5, 8, 22.75),  # using_the_ibm_runtime.ipynb cells 2, 6, 8
+}
+
+
+def jssp_instance(ref, which):
+    """The small JSSP instances of the reference's example notebooks (BASELINE config C1) -> (encoder, Hamiltonian, expected
+    minimum).  Penalties as in every notebook."""
+    spec, limit, n_qubits, best = JSSP_INSTANCES[which]
+    names = sorted({m for job in spec for m, _ in job})
+    machines = {name: ref["Machine"](name=name) for name in names}
+    jobs = []
+    for j, ops in enumerate(spec):
+        jobs.append(ref["Job"](name=f"j{j}", operations=tuple(
+            ref["Operation"](name=f"j{j}op{i}", machine=machines[m], processing_duration=d, job_name=f"j{j}") for i, (m, d) in enumerate(ops))))
+    instance = ref["JobShopSchedulingProblemInstance"](name=which, machines=tuple(machines[n] for n in names), jobs=tuple(jobs))
+    encoder = ref["JSSPDomainWallHamiltonianEncoder"](jssp_instance=instance, makespan_limit=limit, max_opt_value=100, opt_all_operations_share=0.19,
+                                                      encoding_penalty=319, overlap_constraint_penalty=319, precedence_constraint_penalty=275)
+    assert encoder.n_qubits == n_qubits
+    return encoder, encoder.get_problem_hamiltonian(), best
+
+
 def jssp_solver(ref, sampler, executor, random_seed=0):
     """Sampler-only CVaR(0.5) configuration of examples/evqe_jssp_small_examples.ipynb cell 10."""
     from qiskit_algorithms.optimizers import SPSA

@@ -59,14 +59,17 @@ def test_reference_evqe_on_b200_primitives_finds_ground_state(ref, mutex):
         assert evals > 100
 
 
-def test_reference_evqe_jssp_4q_sampler_cvar_on_b200(ref):
-    """BASELINE config C1: the smallest JSSP instance of examples/evqe_jssp_small_examples.ipynb, sampler-only CVaR(0.5)
-    objective, the reference's loop unchanged, B200SamplerV2 underneath."""
+@pytest.mark.parametrize("which", ["4q", "5q", "8q"])
+def test_reference_evqe_jssp_sampler_cvar_on_b200(ref, which):
+    """BASELINE config C1: the small JSSP instances of examples/evqe_jssp_small_examples.ipynb (4 and 5 qubits) and
+    examples/using_the_ibm_runtime.ipynb (8 qubits), sampler-only CVaR(0.5) objective, the reference's loop unchanged,
+    B200SamplerV2 underneath.  The loop must reach the convergence values the notebooks print (63.5 / 61.6 / 22.75 = the minimum
+    diagonal energies, tests/golden/jssp_hamiltonians.json) -- with EVQE seed 0 and sampler seed 7 it does so with the oracle-backed
+    sampler on CPU as well, after the same number of circuit evaluations."""
     from queasars_b200 import B200SamplerV2
 
-    encoder, hamiltonian = reference_loop.jssp_4q(ref)
-    assert encoder.n_qubits == 4
-    sampler = B200SamplerV2(device=0, seed=None)
+    encoder, hamiltonian, best_value = reference_loop.jssp_instance(ref, which)
+    sampler = B200SamplerV2(device=0, seed=7)
     launches0 = sampler.engine.launch_count
     with ThreadPoolExecutor(max_workers=10) as pool:
         solver = reference_loop.jssp_solver(ref, sampler, pool, random_seed=0)
@@ -75,8 +78,8 @@ def test_reference_evqe_jssp_4q_sampler_cvar_on_b200(ref):
         dt = time.perf_counter() - t0
     evals = sum(result.circuit_evaluations)
     best = reference_loop.likeliest_bitstring(result)
-    _log({"case": "C1: 4-qubit JSSP, sampler CVaR(0.5), SPSA", "seconds": dt, "circuit_evaluations": evals, "evals_per_s": evals / dt,
-          "eigenvalue": float(result.eigenvalue), "best": best, "kernel_launches": sampler.engine.launch_count - launches0, "reference": ref["path"]})
+    _log({"case": f"C1: {which} JSSP, sampler CVaR(0.5), SPSA", "seconds": dt, "circuit_evaluations": evals, "evals_per_s": evals / dt,
+          "eigenvalue": float(result.eigenvalue), "expected": best_value, "best": best, "kernel_launches": sampler.engine.launch_count - launches0,
+          "reference": ref["path"]})
     assert sampler.engine.launch_count > launches0
-    assert best in ("0011", "1100")
-    assert result.eigenvalue == pytest.approx(63.5, abs=1.0)
+    assert result.eigenvalue == pytest.approx(best_value, abs=1e-6)
