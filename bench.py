@@ -433,6 +433,7 @@ def run_b200(args):
             line["c3_24q_tfim"] = guarded(lambda: c3_probe(local_rank))
             line["c4_26q_sampler"] = guarded(lambda: c4_probe(local_rank))
             line["e2e_threaded"] = guarded(lambda: threaded_probe(local_rank, operator, circuits, params, values, args))
+            line["c1_jssp_reference_loop"] = guarded(lambda: c1_probe(local_rank))
         else:
             line["strong"] = guarded(lambda: strong_probe(dist, rank, world, engine, plans, ham, params, values, args, barrier, max_over_ranks))
             batch.close()
@@ -613,6 +614,36 @@ def c4_probe(device):
     out["max_probability_mass_between_mismatched_draws"] = max(between) if between else 0.0
     out["mismatches_are_cdf_neighbours"] = bool(all(m < 1e-10 for m in between) and all(probs[got[i]] > 0 for i in flips))
     out["shots_checked"] = shots
+    return out
+
+
+def c1_probe(device):
+    """BASELINE config 1: the reference's OWN ``EVQEMinimumEigensolver`` loop (unmodified package from the git-ignored
+    ``baseline/_ref``, staged by tools/stage_reference.py) on the small JSSP instances of its example notebooks, sampler-only
+    CVaR(0.5) objective as in examples/evqe_jssp_small_examples.ipynb cell 10, with ``B200SamplerV2`` handed to it inside
+    ``ConfiguredSamplerV2``.  Reports the objective reached (notebook values: 63.5 / 61.6 / 22.75), the circuit evaluations the
+    loop spent and its wall time (the loop itself -- Python threads, SPSA, genome operators -- is the reference's)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    ref_path = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_path, "queasars", "__init__.py")):
+        return {"skipped": "baseline/_ref not staged (python tools/stage_reference.py in the build container)"}
+    from queasars_b200 import B200SamplerV2
+    from tests import reference_loop
+
+    ref = reference_loop.import_reference(ref_path)
+    out = {}
+    for which in ("4q", "5q", "8q"):
+        _, hamiltonian, best = reference_loop.jssp_instance(ref, which)
+        sampler = B200SamplerV2(device=device, seed=7)
+        with ThreadPoolExecutor(max_workers=10) as pool:
+            solver = reference_loop.jssp_solver(ref, sampler, pool, random_seed=0)
+            t0 = time.perf_counter()
+            result = solver.compute_minimum_eigenvalue(operator=hamiltonian)
+            dt = time.perf_counter() - t0
+        evals = int(sum(result.circuit_evaluations))
+        out[which] = {"objective": float(result.eigenvalue), "notebook_value": best, "circuit_evaluations": evals, "seconds": dt, "evals_per_s": evals / dt,
+                      "generations": len(result.circuit_evaluations)}
     return out
 
 

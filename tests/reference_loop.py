@@ -17,11 +17,11 @@ def locate_reference():
     return None
 
 
-def import_reference():
+def import_reference(path=None):
     """-> namespace of the reference classes the tests need (imports the unmodified package)."""
     from queasars_b200 import qiskit_compat
 
-    path = locate_reference()
+    path = locate_reference() if path is None else path
     if path is None:
         raise RuntimeError("reference package not found")
     qiskit_compat.install()
