@@ -32,6 +32,7 @@ multi-rank host logic on CPU with the gloo backend.
 """
 from __future__ import annotations
 
+import dataclasses
 import math
 import os
 from typing import Optional, Sequence
@@ -42,7 +43,7 @@ from .gate_list import DENSE, GateList, KernelOp
 
 
 def _remap(op: KernelOp, position: Sequence[int]) -> KernelOp:
-    return KernelOp(op.kind, position[op.target], -1 if op.control < 0 else position[op.control], op.gamma, op.theta, op.phi, op.lam)
+    return dataclasses.replace(op, target=position[op.target], control=-1 if op.control < 0 else position[op.control])
 
 
 def _state_ptr(state) -> int:
