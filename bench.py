@@ -375,7 +375,16 @@ def run_b200(args):
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
     # FP64 side of the roofline: DFMA-class instructions the applied gates need, counted from the plans' own ops (after the
     # front end's rewrites), against the sustained DFMA issue rate measured on this pool's B200 (tools/fp64_peak.cu).
-    dfma = sum(p.dfma_per_amplitude for p in plans) * float(1 << N_QUBITS)
+    from queasars_b200 import gate_list as _gl
+    from queasars_b200 import schedule as _sc
+
+    dfma = 0.0
+    from queasars_b200 import engine as _eng
+
+    for c in circuits:
+        ops = _eng.rewritten(estimator._cache.gates_for(c)["gates"], drop_final_phases=True).ops
+        _, remaining = _sc.split_product_prefix(ops, N_QUBITS)
+        dfma += sum(_gl.dfma_per_amplitude(ops[i]) for i in remaining) * float(1 << N_QUBITS)
     fp64_peak = 16.9e12
     fp64_rate = dfma / (ms_per_step * 1e-3)
     n_plan_ops = float(np.mean([p.n_ops for p in plans]))
@@ -464,7 +473,7 @@ def gate_apply_probe(engine, peak):
     def measure(gates, params, reps):
         # planned like the evaluators plan for a diagonal observable / sampling (engine.rewritten: trailing phases deferred)
         plan = engine.compile(gates, drop_final_phases=True)
-        sweeps = eng_mod.encoded_plan(eng_mod.rewritten(gates, True), engine.tile_bits, engine.reg_bits, True)[3][0]
+        _, _, _, (sweeps, _, _, _, _) = eng_mod.encoded_plan(eng_mod.rewritten(gates, True), engine.tile_bits, engine.reg_bits, True)
         rb = engine.resident_batch([plan], None)
         rb.set_params([params])
         for _ in range(2):

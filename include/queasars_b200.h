@@ -47,8 +47,6 @@ extern "C" {
 
 #define QB_OP_DENSE 0 /* e^{i gamma} U(theta,phi,lam) on target [, control]            */
 #define QB_OP_DIAG 1  /* diag(e^{i gamma}, e^{i(gamma+lam)}) on target [, control]     */
-#define QB_OP_NEG_CONTROL 0x80 /* qb_pass_op.kind bit 7 (dense ops): the control acts on |0> instead of |1> -- the control = 0 half
-                                  of a fused "select" pair (queasars_b200/schedule.py: fuse_selects) */
 
 /* --- sweep program records (flat arrays produced by the host-side planner) ------------------------- */
 typedef struct qb_sweep {
@@ -91,8 +89,7 @@ typedef struct qb_op_angles {
     double coeff2[4];
     double cnst[4];
     int32_t kind;
-    int32_t pad; /* select fusion: k > 0: the op's matrix is U(this) . M(op k - 1);  k < 0: M(op -k - 1) . U(this);  0: U(this).
-                    The named op must be a dense op without a product of its own. */
+    int32_t pad;
 } qb_op_angles;
 
 typedef struct qb_context qb_context;

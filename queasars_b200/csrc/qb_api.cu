@@ -860,17 +860,8 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
             for (int o = ps.op_begin; o < ps.op_end; ++o) {
                 const qb_pass_op& po = pass_ops[o];
                 if (po.op_index < 0 || po.op_index >= n_ops) return fail(QB_ERR_INVALID, "op index out of range");
-                const int kind = po.kind & 0x7f;
-                const bool neg = (po.kind & QB_OP_NEG_CONTROL) != 0;
-                if (kind != QB_OP_DENSE && kind != QB_OP_DIAG) return fail(QB_ERR_INVALID, "unknown op kind");
-                if (kind == QB_OP_DENSE && (po.tgt_kind != QB_K_REG || po.tgt_pos >= reg_bits))
+                if (po.kind == QB_OP_DENSE && (po.tgt_kind != QB_K_REG || po.tgt_pos >= reg_bits))
                     return fail(QB_ERR_INVALID, "dense op target must be a register bit");
-                if (neg) {  // negated control: dense ops only; under a register-bit control only gates with a real first column have a body
-                    const qb_op_angles& ang = ops[po.op_index];
-                    const bool real10 = ang.pad == 0 && ang.slot[0] < 0 && ang.slot2[0] < 0 && ang.cnst[0] == 0.0 && ang.slot[2] < 0 && ang.slot2[2] < 0 && ang.cnst[2] == 0.0;
-                    if (kind != QB_OP_DENSE || po.ctrl_kind == QB_K_NONE || (po.ctrl_kind == QB_K_REG && !real10))
-                        return fail(QB_ERR_INVALID, "negated control on an op that has no such kernel body");
-                }
                 auto bad = [&](int kind, int pos) {
                     if (kind == QB_K_REG) return pos >= reg_bits;
                     if (kind == QB_K_THREAD) return pos >= tile_bits;
@@ -883,25 +874,19 @@ int qb_plan_create(qb_context* ctx, int n_qubits, int dtype, int tile_bits, int 
                 auto gq = [&](int kind, int pos) { return kind == QB_K_THREAD ? sw.tile_qubits[pos] : (kind == QB_K_EXT ? pos : 0xFF); };
                 const int cb = po.ctrl_kind == QB_K_REG ? int(po.ctrl_pos) : -1;
                 int variant, tq = 0xFF;
-                if (kind == QB_OP_DENSE) variant = 6 * po.tgt_pos + cb + 1;
+                if (po.kind == QB_OP_DENSE) variant = 6 * po.tgt_pos + cb + 1;
                 else if (cb >= 0) variant = 40, tq = gq(po.tgt_kind, po.tgt_pos);
                 else if (po.tgt_kind == QB_K_REG) variant = 33 + po.tgt_pos;
                 else variant = 32, tq = gq(po.tgt_kind, po.tgt_pos);
-                if (kind == QB_OP_DENSE && cb == int(po.tgt_pos)) return fail(QB_ERR_INVALID, "control equals target");
+                if (po.kind == QB_OP_DENSE && cb == int(po.tgt_pos)) return fail(QB_ERR_INVALID, "control equals target");
                 if (po.variant != variant || po.ctrl_qubit != gq(po.ctrl_kind, po.ctrl_pos) || po.tgt_qubit != tq)
                     return fail(QB_ERR_INVALID, "pre-decoded dispatch fields are inconsistent");
             }
         }
     }
-    for (int o = 0; o < n_ops; ++o) {
+    for (int o = 0; o < n_ops; ++o)
         for (int j = 0; j < 4; ++j)
             if (ops[o].slot[j] >= n_params || ops[o].slot2[j] >= n_params) return fail(QB_ERR_INVALID, "angle slot out of range");
-        if (ops[o].pad != 0) {  // bound product with another op (select fusion)
-            const int other = (ops[o].pad > 0 ? ops[o].pad : -ops[o].pad) - 1;
-            if (other >= n_ops || other == o || ops[o].kind != QB_OP_DENSE || ops[other].kind != QB_OP_DENSE || ops[other].pad != 0)
-                return fail(QB_ERR_INVALID, "bad matrix-product reference in an op");
-        }
-    }
     bool has_init = false;
     if (init_ops) {
         std::vector<char> used(size_t(std::max(n_ops, 1)), 0);

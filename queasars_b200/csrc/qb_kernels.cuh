@@ -127,9 +127,7 @@ __device__ __forceinline__ double ld_table(const double* p) {
 // dispatch word; skipping the two FMAs is bit-identical to executing them with m00.y = +0.
 // REAL10: the bottom-left entry is real as well (phi == 0: the R_Y(theta) * D(lam) form every uncontrolled gate has after the
 // front end's phase deferral, gate_list.py: defer_phases) -- two more multiply-adds vanish, 12 per pair.
-// NEG: a register-bit control acts on the pairs whose control bit is CLEAR (the control = 0 half of a fused select pair,
-// schedule.py: fuse_selects).
-template <typename T, int R, int B, int CB, bool REAL00 = false, bool REAL10 = false, bool NEG = false>
+template <typename T, int R, int B, int CB, bool REAL00 = false, bool REAL10 = false>
 __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type m00, const typename Cx<T>::type m01,
                                             const typename Cx<T>::type m10, const typename Cx<T>::type m11) {
     constexpr int kNReg = 1 << R;
@@ -142,7 +140,7 @@ __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], c
 #pragma unroll
     for (int j = 0; j < kNReg; ++j) {
         if (j & (1 << B)) continue;
-        if (CB >= 0 && (((j >> (CB >= 0 ? CB : 0)) & 1) == (NEG ? 1 : 0))) continue;
+        if (CB >= 0 && !(j & (1 << (CB >= 0 ? CB : 0)))) continue;
         const C x = a[j], y = a[j | (1 << B)];
         T t0 = m01.x * y.x;
         T t1 = m01.x * y.y;
@@ -174,7 +172,7 @@ __device__ __forceinline__ void apply_dense(typename Cx<T>::type (&a)[1 << R], c
 #pragma unroll
         for (int j = 0; j < kNReg; ++j) {
             if (j & (1 << B)) continue;
-            if (CB >= 0 && (((j >> (CB >= 0 ? CB : 0)) & 1) == (NEG ? 1 : 0))) continue;
+            if (CB >= 0 && !(j & (1 << (CB >= 0 ? CB : 0)))) continue;
             base[n++] = j;
         }
     }
@@ -266,9 +264,6 @@ constexpr int kMaxInitQubits = 64;
 // dispatch word: variant | cpos << 6 | dpos << 11 | dflag << 16 | cb << 17 | tb << 20 | treg << 23
 //   variant bit 5 (dense ops): the matrix's top-left entry is real (gamma == 0) -> 14 instead of 16 multiply-adds per pair
 //   variant 48 + b (uncontrolled dense on register bit b): the whole first column is real (gamma == phi == 0) -> 12
-//   variant 52 + c (c enumerates (target, control) register bits like the controlled variants): such a gate under a NEGATED
-//         register-bit control -- the control = 0 half of a fused select pair (schedule.py: fuse_selects)
-//   bit 24: negated thread-bit / external control (the op runs where the control bit is 0)
 //   cpos  tile-local position of a thread-bit control; 31 = none (bit 31 of the test word is always set), 30 = an external
 //         control that is 0 for this tile (bit 30 is never set)
 //   dpos  tile-local position of a thread-bit diagonal target; 31 = use dflag (external target, resolved per tile)
@@ -287,9 +282,9 @@ constexpr size_t sweep_smem_bytes() {
 }
 
 // apply_dense for a (B, CB) pair that may not exist for this R (keeps the case lists below uniform)
-template <typename T, int R, int B, int CB, bool REAL00, bool REAL10 = false, bool NEG = false>
+template <typename T, int R, int B, int CB, bool REAL00, bool REAL10 = false>
 __device__ __forceinline__ void dense_if(typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
-    if constexpr (B < R && CB < R && B != CB) apply_dense<T, R, B, CB, REAL00, REAL10, NEG>(a, m[0], m[1], m[2], m[3]);
+    if constexpr (B < R && CB < R && B != CB) apply_dense<T, R, B, CB, REAL00, REAL10>(a, m[0], m[1], m[2], m[3]);
 }
 
 // uncontrolled dense gate on register bit v (< R): two predictable branches
@@ -312,10 +307,10 @@ __device__ __forceinline__ void dense_by_bit(uint32_t v, typename Cx<T>::type (&
 // combinations that do not exist for this R get labels that never match
 template <int R> __host__ __device__ constexpr int ctrl_label(int B, int k) { return (B < R && k < R - 1) ? B * (R - 1) + k : 100 + 4 * B + k; }
 
-template <typename T, int R, bool REAL00, bool REAL10 = false, bool NEG = false>
+template <typename T, int R, bool REAL00>
 __device__ __forceinline__ void ctrl_by_code(uint32_t c, typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type* __restrict__ m) {
     switch (c) {
-#define QB_C(B, K_) case ctrl_label<R>(B, K_): dense_if<T, R, B, (K_ < B ? K_ : K_ + 1), REAL00, REAL10, NEG>(a, m); break;
+#define QB_C(B, K_) case ctrl_label<R>(B, K_): dense_if<T, R, B, (K_ < B ? K_ : K_ + 1), REAL00>(a, m); break;
         QB_C(0, 0) QB_C(0, 1) QB_C(0, 2)
         QB_C(1, 0) QB_C(1, 1) QB_C(1, 2)
         QB_C(2, 0) QB_C(2, 1) QB_C(2, 2)
@@ -342,10 +337,6 @@ __device__ __forceinline__ void apply_op(uint32_t word, uint32_t e_thr, typename
     // then one with a real top-left entry only (bit 5 of the variant).
     if ((variant ^ 48u) < uint32_t(R)) {
         dense_by_bit<T, R, true, true>(variant & 3u, a, m);
-        return;
-    }
-    if (variant >= 52u) {  // real-first-column gate on the pairs whose REGISTER-bit control is 0 (control = 0 half of a select pair)
-        ctrl_by_code<T, R, true, true, true>(variant - 52u, a, m);
         return;
     }
     if ((variant ^ 32u) < uint32_t(R)) {
@@ -446,21 +437,19 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             uint32_t w = 0, x = 0xffffu;
             if (i < n_sop) {
                 const qb_pass_op po = ge.pass_ops[op_begin + i];
-                uint32_t cpos = 31, dpos = 31, cb = 0, tb = 0, treg = 0, variant, extc = 0xff, extt = 0xff, negc = 0;
-                const bool neg = (po.kind & QB_OP_NEG_CONTROL) != 0;
-                if (po.ctrl_kind == QB_K_THREAD) cpos = po.ctrl_pos, negc = neg;
-                else if (po.ctrl_kind == QB_K_EXT) extc = po.ctrl_pos, negc = neg;
+                uint32_t cpos = 31, dpos = 31, cb = 0, tb = 0, treg = 0, variant, extc = 0xff, extt = 0xff;
+                if (po.ctrl_kind == QB_K_THREAD) cpos = po.ctrl_pos;
+                else if (po.ctrl_kind == QB_K_EXT) extc = po.ctrl_pos;
                 const int rcb = (po.ctrl_kind == QB_K_REG) ? int(po.ctrl_pos) : -1;
-                if ((po.kind & 0x7f) == QB_OP_DENSE) {
+                if (po.kind == QB_OP_DENSE) {
                     const int b = po.tgt_pos;
-                    const uint32_t code = rcb < 0 ? 0u : uint32_t(b * (R - 1) + (rcb < b ? rcb : rcb - 1));
+                    variant = rcb < 0 ? uint32_t(b) : uint32_t(R + b * (R - 1) + (rcb < b ? rcb : rcb - 1));
                     const qb_op_angles& ang = ge.angles[po.op_index];
-                    // gamma == 0 (and no bound product): m00 = cos(theta / 2) is real; phi == 0 too: m10 = sin(theta / 2) is real
-                    const bool real00 = ang.pad == 0 && ang.slot[0] < 0 && ang.slot2[0] < 0 && ang.cnst[0] == 0.0;
-                    const bool real10 = real00 && ang.slot[2] < 0 && ang.slot2[2] < 0 && ang.cnst[2] == 0.0;
-                    if (rcb < 0) variant = uint32_t(b) | (real00 ? 32u : 0u) | (real10 ? 16u : 0u);
-                    else if (neg) variant = 52u + code;  // (qb_plan_create checked that the gate has a real first column)
-                    else variant = (uint32_t(R) + code) | (real00 ? 32u : 0u);
+                    if (ang.slot[0] < 0 && ang.slot2[0] < 0 && ang.cnst[0] == 0.0) {
+                        variant |= 32u;  // gamma == 0: m00 = cos(theta / 2) is real
+                        // phi == 0 too: m10 = sin(theta / 2) is real (uncontrolled gates only have such bodies)
+                        if (rcb < 0 && ang.slot[2] < 0 && ang.slot2[2] < 0 && ang.cnst[2] == 0.0) variant |= 16u;
+                    }
                 } else {
                     if (po.tgt_kind == QB_K_THREAD) dpos = po.tgt_pos;
                     else if (po.tgt_kind == QB_K_EXT) extt = po.tgt_pos;
@@ -474,7 +463,7 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                         variant = uint32_t(v_diag_out<R>());
                     }
                 }
-                w = variant | (cpos << 6) | (dpos << 11) | (cb << 17) | (tb << 20) | (treg << 23) | (negc << 24);
+                w = variant | (cpos << 6) | (dpos << 11) | (cb << 17) | (tb << 20) | (treg << 23);
                 x = extc | (extt << 8);
                 if (x != 0xffffu) s_has_ext = 1;
             }
@@ -571,10 +560,7 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                 uint32_t w = s_word0[tid];
                 const uint32_t x = s_ext[tid];
                 const uint32_t qc = x & 0xffu, qt = (x >> 8) & 0xffu;
-                if (qc != 0xffu) {  // external control: decided per tile (with its polarity), the word then carries "always" / "never"
-                    const uint32_t run = uint32_t((gbase >> qc) & 1ull) ^ ((w >> 24) & 1u);
-                    w = (w & ~((31u << 6) | (1u << 24))) | ((run ? 31u : 30u) << 6);
-                }
+                if (qc != 0xffu && !((gbase >> qc) & 1ull)) w = (w & ~(31u << 6)) | (30u << 6);
                 if (qt != 0xffu) w |= uint32_t((gbase >> qt) & 1ull) << 16;
                 dst[tid] = w;
             }
@@ -650,7 +636,7 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             for (; o < o_end; ++o) {
                 const uint32_t word = word_next;
                 word_next = s_w[o + 1];  // prefetch the next dispatch word behind this op's arithmetic
-                if (!(((test >> ((word >> 6) & 31u)) ^ (word >> 24)) & 1u)) continue;  // control bit (bit 24: negated) says skip
+                if (!((test >> ((word >> 6) & 31u)) & 1u)) continue;
                 apply_op<T, R>(word, e_thr, a, s_mat + o * 4);
             }
 
@@ -728,35 +714,13 @@ __device__ __forceinline__ void bind_matrix(const qb_op_angles& ang, const doubl
     }
 }
 
-// Bound matrix of op `o`, including the product with the op named by qb_op_angles.pad (select fusion):
-//   pad = k > 0:  U(o) . M(k - 1)      pad = -k < 0:  M(k - 1) . U(o)
-__device__ __forceinline__ void bind_op(const qb_op_angles* __restrict__ angles, int o, const double* __restrict__ params, double* __restrict__ m) {
-    const qb_op_angles& ang = angles[o];
-    bind_matrix(ang, params, m);
-    if (ang.pad == 0) return;
-    double other[8], l[8], r[8];
-    bind_matrix(angles[(ang.pad > 0 ? ang.pad : -ang.pad) - 1], params, other);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) l[i] = ang.pad > 0 ? m[i] : other[i], r[i] = ang.pad > 0 ? other[i] : m[i];
-    // (re, im) pairs, row-major: [0,1] = 00, [2,3] = 01, [4,5] = 10, [6,7] = 11
-#pragma unroll
-    for (int row = 0; row < 2; ++row)
-#pragma unroll
-        for (int col = 0; col < 2; ++col) {
-            const double ar = l[4 * row], ai = l[4 * row + 1], br = l[4 * row + 2], bi = l[4 * row + 3];
-            const double cr = r[2 * col], ci = r[2 * col + 1], dr = r[4 + 2 * col], di = r[4 + 2 * col + 1];
-            m[4 * row + 2 * col] = ar * cr - ai * ci + br * dr - bi * di;
-            m[4 * row + 2 * col + 1] = ar * ci + ai * cr + br * di + bi * dr;
-        }
-}
-
 // matrices[0 .. n_ops) by op index (read by the product-state start), matrices[n_ops .. n_ops + n_pass_ops) in pass-op
 // order (what a sweep stages: one contiguous, index-free copy)
 __global__ void bind_kernel(const BatchEntry* __restrict__ entries) {
     const BatchEntry& en = entries[blockIdx.x];
-    for (int o = threadIdx.x; o < en.n_ops; o += blockDim.x) bind_op(en.angles, o, en.params, en.matrices + size_t(o) * 8);
+    for (int o = threadIdx.x; o < en.n_ops; o += blockDim.x) bind_matrix(en.angles[o], en.params, en.matrices + size_t(o) * 8);
     for (int i = threadIdx.x; i < en.n_pass_ops; i += blockDim.x)
-        bind_op(en.angles, en.pass_ops[i].op_index, en.params, en.matrices + (size_t(en.n_ops) + size_t(i)) * 8);
+        bind_matrix(en.angles[en.pass_ops[i].op_index], en.params, en.matrices + (size_t(en.n_ops) + size_t(i)) * 8);
     // product-state start: per qubit the two amplitudes (re, im, re, im) of its initial single-qubit state
     if (en.init_ops != nullptr) {
         double* init_vec = en.matrices + (size_t(en.n_ops) + size_t(en.n_pass_ops)) * 8;

@@ -54,20 +54,15 @@ _encoded_lock = threading.Lock()
 
 
 def encoded_plan(gates: GateList, tile_bits: int, reg_bits: int, from_zero_state: bool):
-    """-> (n_sweeps, n_passes, n_pass_ops, (sweeps, passes, pass_ops, angles, init_ops), n_ops, dfma) of ``schedule.plan_circuit``:
-    ``n_ops`` = size of the plan's op table (the circuit's ops + what select fusion appended), ``dfma`` = FP64 multiply-add-class
-    instructions per amplitude the planned ops cost (roofline accounting)."""
+    """-> (n_sweeps, n_passes, n_pass_ops, (sweeps, passes, pass_ops, angles, init_ops)) of ``schedule.plan_circuit``."""
     key = (int(tile_bits), int(reg_bits), bool(from_zero_state), gates.structure_key())
     with _encoded_lock:
         hit = _encoded_plans.get(key)
     if hit is not None:
         return hit
     plan = schedule.plan_circuit(gates.ops, gates.n_qubits, tile_bits=tile_bits, reg_bits=reg_bits, product_prefix=from_zero_state)
-    arrays = schedule.encode_plan(plan)
-    from .gate_list import dfma_per_amplitude
-
-    dfma = sum(dfma_per_amplitude(plan.ops[po.op_index]) for sw in plan.sweeps for ps in sw.passes for po in ps.ops)
-    hit = (len(arrays[0]), len(arrays[1]), sum(s.n_ops for s in plan.sweeps), arrays, len(plan.ops), dfma)
+    arrays = schedule.encode_plan(plan, gates.ops)
+    hit = (len(arrays[0]), len(arrays[1]), sum(s.n_ops for s in plan.sweeps), arrays)
     with _encoded_lock:
         if len(_encoded_plans) > 4096:
             _encoded_plans.clear()
@@ -76,13 +71,12 @@ def encoded_plan(gates: GateList, tile_bits: int, reg_bits: int, from_zero_state
 
 
 class PlanHandle:
-    __slots__ = ("plan_id", "n_qubits", "n_params", "n_ops", "n_sweeps", "n_passes", "dtype", "prefix", "dfma_per_amplitude", "__weakref__")
+    __slots__ = ("plan_id", "n_qubits", "n_params", "n_ops", "n_sweeps", "n_passes", "dtype", "prefix", "__weakref__")
 
     def __init__(self, plan_id, n_qubits, n_params, n_ops, n_sweeps, n_passes, dtype):
         self.plan_id, self.n_qubits, self.n_params = plan_id, n_qubits, n_params
         self.n_ops, self.n_sweeps, self.n_passes, self.dtype = n_ops, n_sweeps, n_passes, dtype
         self.prefix = None  # PlanHandle of the parameter-free prefix this plan starts from (kept alive with it)
-        self.dfma_per_amplitude = 0.0  # FP64 multiply-add-class instructions per amplitude of the planned ops (n_ops = ops in passes)
 
 
 class HamiltonianHandle:
@@ -250,16 +244,15 @@ class Engine:
             hit = self._plan_cache.get(key) if cache else None
         if hit is not None:
             return hit
-        _, _, n_pass_ops, (sweeps, passes, pass_ops, angles, init_ops), n_ops, dfma = encoded_plan(gates, self.tile_bits, self.reg_bits, from_zero_state)
+        _, _, n_pass_ops, (sweeps, passes, pass_ops, angles, init_ops) = encoded_plan(gates, self.tile_bits, self.reg_bits, from_zero_state)
         plan_id = c_int64()
         _native.check(
             self._lib.qb_plan_create(
-                self._ctx, gates.n_qubits, code, self.tile_bits, self.reg_bits, gates.n_params, n_ops, _native.ptr(angles), len(sweeps), _native.ptr(sweeps),
+                self._ctx, gates.n_qubits, code, self.tile_bits, self.reg_bits, gates.n_params, len(gates.ops), _native.ptr(angles), len(sweeps), _native.ptr(sweeps),
                 len(passes), _native.ptr(passes), n_pass_ops, _native.ptr(pass_ops), _native.ptr(init_ops), byref(plan_id),
             )
         )
-        handle = PlanHandle(plan_id.value, gates.n_qubits, gates.n_params, n_pass_ops, len(sweeps), len(passes), code)
-        handle.dfma_per_amplitude = dfma
+        handle = PlanHandle(plan_id.value, gates.n_qubits, gates.n_params, len(gates.ops), len(sweeps), len(passes), code)
         weakref.finalize(handle, self._release_plan, self._lib, self._ctx, plan_id.value, self._finalizer)
         if cache:
             with self._lock:

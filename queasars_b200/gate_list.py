@@ -87,9 +87,6 @@ class KernelOp:
     theta: Angle = ZERO
     phi: Angle = ZERO
     lam: Angle = ZERO
-    # produced by the planner's select fusion only (schedule.fuse_selects):
-    neg: bool = False  # the control acts on |0> instead of |1>
-    mul_op: int = 0  # k > 0: matrix = U(self) . M(ops[k - 1]);  k < 0: matrix = M(ops[-k - 1]) . U(self);  0: matrix = U(self)
 
     @property
     def angles(self) -> tuple[Angle, Angle, Angle, Angle]:
@@ -166,8 +163,8 @@ def dfma_per_amplitude(op: KernelOp) -> float:
     if op.kind == DIAG:
         per = 4.0
     else:
-        real00 = op.gamma.is_zero and op.mul_op == 0
-        real10 = real00 and op.phi.is_zero and (op.control < 0 or op.neg)  # REAL10 bodies: uncontrolled and negated-control ops
+        real00 = op.gamma.slot < 0 and op.gamma.const == 0.0
+        real10 = real00 and op.phi.is_zero and op.control < 0  # only the uncontrolled REAL10 bodies are compiled
         per = 6.0 if real10 else (7.0 if real00 else 8.0)
     return per * (1.0 if op.control < 0 else 0.5)
 

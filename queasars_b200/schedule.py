@@ -20,7 +20,6 @@ the circuit's unitaries; reordering commuting gates changes results only at the 
 """
 from __future__ import annotations
 
-import dataclasses
 import os
 from dataclasses import dataclass, field
 from typing import Sequence
@@ -48,10 +47,6 @@ PREFER_CONTROLS_ON_WARP_BITS = os.environ.get("QB_CTRL_WARP", "1") != "0"  # A/B
 # free: spread the arithmetic evenly over the sweeps (without adding a sweep) instead of packing the first ones full.
 BALANCE_MIN_QUBITS = int(os.environ.get("QB_BALANCE_MIN_QUBITS", "22"))
 BALANCE_SLACK = (1.0, 1.1, 1.25, 1.5)
-# Select fusion (fuse_selects): an uncontrolled gate and a controlled gate that follow each other on one target qubit become ONE
-# pair of complementary-controlled gates -- control 0: the uncontrolled matrix, control 1: the product of both -- so the control = 1
-# half of the state is updated once instead of twice.
-FUSE_SELECTS = os.environ.get("QB_FUSE_SELECT", "1") != "0"
 
 # position kinds in the encoded program
 K_NONE, K_REG, K_THREAD, K_EXT = 0, 1, 2, 3
@@ -65,7 +60,6 @@ class PassOp:
     tgt_pos: int
     ctrl_kind: int
     ctrl_pos: int
-    neg: bool = False  # negated control (qb_pass_op.kind bit 7)
 
 
 @dataclass
@@ -96,7 +90,6 @@ class CircuitPlan:
     sweeps: list[SweepPlan]
     n_ops: int
     init_ops: list[int] = field(default_factory=list)  # per (padded) qubit: op giving its initial state, or -1
-    ops: list = field(default_factory=list)  # the op table the indices refer to: the circuit's ops + the ones select fusion added
 
     @property
     def n_passes(self) -> int:
@@ -289,7 +282,7 @@ def _plan_passes(ops: Sequence[KernelOp], chosen: list[int], tile_qubits: list[i
             if op.kind == DENSE:
                 assert tk == K_REG
             ck, cpos = (K_NONE, 0) if op.control < 0 else locate(op.control)
-            plan.ops.append(PassOp(i, op.kind, tk, tpos, ck, cpos, op.neg))
+            plan.ops.append(PassOp(i, op.kind, tk, tpos, ck, cpos))
         passes.append(plan)
     for a, b in zip(passes, passes[1:]):
         a.warp_local_exchange = n_warp > 0 and a.thread_bits[5:] == b.thread_bits[5:]
@@ -324,63 +317,6 @@ def split_product_prefix(ops: Sequence[KernelOp], n_qubits: int) -> tuple[list[i
     return init_ops, remaining
 
 
-def _is_real10(op: KernelOp) -> bool:
-    """Uncontrolled dense gate in R_Y(theta) D(lam) form (gamma == phi == 0: what phase deferral leaves): real first column."""
-    return op.kind == DENSE and op.control < 0 and op.mul_op == 0 and op.gamma.is_zero and op.phi.is_zero
-
-
-def fuse_selects(ops: Sequence[KernelOp], remaining: Sequence[int]) -> tuple[list[KernelOp], list[int]]:
-    """Select fusion on the ops still to be applied (after the product-state prefix was split off).
-
-    Where an uncontrolled R_Y D gate ``A`` and a controlled gate ``CU`` (control c) follow each other on target qubit t with
-    nothing else touching t in between -- in either order -- the two are replaced, at the position of the controlled gate, by
-        control = 0 :  A                      (a negated-control op)
-        control = 1 :  U . A   resp.  A . U   (one bound 2x2 product, ``mul_op``)
-    which is the same unitary (the uncontrolled gate commutes with everything between that does not touch t) but updates the
-    control = 1 half of the state once instead of twice: 12 + 16 instead of 12 + 12 + 14 multiply-adds per amplitude pair there.
-    EVQE layers put exactly one gate on every qubit, so a rotation next to a controlled rotation on the same qubit is the common
-    case (396 fusions in the 1 778 gates of the bench population, -12 % FP64 work).  Returns the extended op table (new ops are
-    appended, indices of the old ones stay valid) and the new application order."""
-    table = list(ops)
-    seq: list[list[int]] = []  # application order; an element holds one op or one fused pair
-    fused: list[bool] = []
-    last_touch: dict[int, int] = {}  # qubit -> index into seq of the last element touching it
-    for i in remaining:
-        op = table[i]
-        t, c = op.target, op.control
-        j = last_touch.get(t)
-        done = False
-        if op.kind == DENSE and j is not None and not fused[j] and len(seq[j]) == 1:
-            prev = table[seq[j][0]]
-            if prev.kind == DENSE and prev.target == t and not prev.neg and prev.mul_op == 0 and not op.neg and op.mul_op == 0:
-                if c >= 0 and _is_real10(prev):
-                    # A then CU: both go to CU's position (A commutes with everything in between: nothing there touches t)
-                    ia = len(table)
-                    table.append(dataclasses.replace(prev, control=c, neg=True))
-                    table.append(dataclasses.replace(op, mul_op=ia + 1))  # U . A
-                    seq[j] = []
-                    seq.append([ia, ia + 1])
-                    fused.append(True)
-                    done = True
-                elif c < 0 and prev.control >= 0 and _is_real10(op):
-                    # CU then A: the pair stays at CU's position (A moves back over ops that do not touch t)
-                    ia = len(table)
-                    table.append(dataclasses.replace(op, control=prev.control, neg=True))
-                    table.append(dataclasses.replace(prev, mul_op=-(ia + 1)))  # A . U
-                    seq[j] = [ia, ia + 1]
-                    fused[j] = True
-                    last_touch[t] = j
-                    continue
-        if not done:
-            seq.append([i])
-            fused.append(False)
-        k = len(seq) - 1
-        last_touch[t] = k
-        if c >= 0:
-            last_touch[c] = k
-    return table, [i for element in seq for i in element]
-
-
 def plan_circuit(
     ops: Sequence[KernelOp],
     n_qubits: int,
@@ -395,8 +331,6 @@ def plan_circuit(
     else:
         init_ops, remaining = [-1] * n_qubits, list(range(len(ops)))
     init_ops = init_ops + [-1] * (n_eff - n_qubits)
-    if FUSE_SELECTS:
-        ops, remaining = fuse_selects(ops, remaining)
 
     def build(rng, p_accept: float = 1.0, caps: Sequence[float] = ()) -> list[SweepPlan]:
         todo, out = list(remaining), []
@@ -481,7 +415,7 @@ def plan_circuit(
         tile_qubits = list(range(tile_bits))
         reg = list(range(tile_bits - reg_bits, tile_bits))
         sweeps.append(SweepPlan(tile_qubits, [PassPlan(reg_bits=reg, thread_bits=_thread_bit_order(reg, tile_bits, low_bits))]))
-    return CircuitPlan(n_qubits, n_eff, tile_bits, reg_bits, low_bits, sweeps, len(ops), init_ops, list(ops))
+    return CircuitPlan(n_qubits, n_eff, tile_bits, reg_bits, low_bits, sweeps, len(ops), init_ops)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -519,10 +453,8 @@ def _predecode(po: PassOp, tile_qubits: Sequence[int]) -> tuple[int, int, int]:
     return 32, cq, global_qubit(po.tgt_kind, po.tgt_pos)
 
 
-def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp] = ()):
-    """-> (sweeps, passes, pass_ops, op_angles, init_ops) arrays.  The op table is the plan's own (``plan.ops``: the circuit's
-    ops plus what select fusion appended); ``ops`` is only used for plans built without one."""
-    ops = plan.ops if plan.ops else ops
+def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp]):
+    """-> (sweeps, passes, pass_ops, op_angles, init_ops) arrays."""
     assert plan.tile_bits <= 16 and plan.reg_bits in (3, REG_BITS)
     sweeps = np.zeros(len(plan.sweeps), dtype=SWEEP_DTYPE)
     passes = np.zeros(plan.n_passes, dtype=PASS_DTYPE)
@@ -539,7 +471,7 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp] = ()):
             passes[pi]["op_begin"] = oi
             for po in ps.ops:
                 rec = pass_ops[oi]
-                rec["op_index"], rec["kind"] = po.op_index, po.kind | (0x80 if po.neg else 0)
+                rec["op_index"], rec["kind"] = po.op_index, po.kind
                 rec["tgt_kind"], rec["tgt_pos"] = po.tgt_kind, po.tgt_pos
                 rec["ctrl_kind"], rec["ctrl_pos"] = po.ctrl_kind, po.ctrl_pos
                 rec["variant"], rec["ctrl_qubit"], rec["tgt_qubit"] = _predecode(po, sw.tile_qubits)
@@ -554,6 +486,5 @@ def encode_plan(plan: CircuitPlan, ops: Sequence[KernelOp] = ()):
             angles[i]["slot"][j], angles[i]["coeff"][j], angles[i]["const"][j] = a.slot, a.coeff, a.const
             angles[i]["slot2"][j], angles[i]["coeff2"][j] = a.slot2, a.coeff2
         angles[i]["kind"] = op.kind
-        angles[i]["pad"] = op.mul_op
     init_ops = np.asarray(plan.init_ops if plan.init_ops else [-1] * plan.n_eff, dtype=np.int32)
     return sweeps, passes, pass_ops, angles, init_ops

@@ -32,7 +32,6 @@ multi-rank host logic on CPU with the gloo backend.
 """
 from __future__ import annotations
 
-import dataclasses
 import math
 import os
 from typing import Optional, Sequence
@@ -43,7 +42,7 @@ from .gate_list import DENSE, GateList, KernelOp
 
 
 def _remap(op: KernelOp, position: Sequence[int]) -> KernelOp:
-    return dataclasses.replace(op, target=position[op.target], control=-1 if op.control < 0 else position[op.control])
+    return KernelOp(op.kind, position[op.target], -1 if op.control < 0 else position[op.control], op.gamma, op.theta, op.phi, op.lam)
 
 
 def _state_ptr(state) -> int:

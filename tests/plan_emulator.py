@@ -10,20 +10,8 @@ from queasars_b200.gate_list import DENSE, DIAG
 from queasars_b200.schedule import K_EXT, K_NONE, K_REG, K_THREAD
 
 
-def op_matrix(angle_rec, params, angles=None):
-    """Bound 2x2 matrix of one op-angle record (two-term affine angles); with ``angles`` given, the bound product of a fused
-    select op (qb_op_angles.pad) is applied like bind_op in csrc/qb_kernels.cuh."""
-    vals = [
-        angle_rec["const"][j]
-        + (angle_rec["coeff"][j] * params[angle_rec["slot"][j]] if angle_rec["slot"][j] >= 0 else 0.0)
-        + (angle_rec["coeff2"][j] * params[angle_rec["slot2"][j]] if angle_rec["slot2"][j] >= 0 else 0.0)
-        for j in range(4)
-    ]
-    mul = int(angle_rec["pad"]) if angles is not None else 0
-    if mul:
-        own = op_matrix(angle_rec, params)
-        other = op_matrix(angles[abs(mul) - 1], params)
-        return own @ other if mul > 0 else other @ own
+def op_matrix(angle_rec, params):
+    vals = [angle_rec["const"][j] + (angle_rec["coeff"][j] * params[angle_rec["slot"][j]] if angle_rec["slot"][j] >= 0 else 0.0) for j in range(4)]
     g, t, p, l = vals
     if angle_rec["kind"] == DIAG:
         return np.array([[cmath.exp(1j * g), 0], [0, cmath.exp(1j * (g + l))]])
@@ -63,8 +51,7 @@ def run_program(encoded, n_eff, tile_bits, params, state=None, reg_bits=4):
                 reg = [int(b) for b in ps["reg_bits"][:reg_bits]]
                 assert len(set(reg)) == reg_bits and all(0 <= b < tile_bits for b in reg)
                 for po in pass_ops[ps["op_begin"] : ps["op_end"]]:
-                    m = op_matrix(angles[po["op_index"]], params, angles)
-                    kind, neg = int(po["kind"]) & 0x7F, bool(int(po["kind"]) & 0x80)
+                    m = op_matrix(angles[po["op_index"]], params)
 
                     def bit_of(kind, pos):
                         kind, pos = int(kind), int(pos)
@@ -79,10 +66,7 @@ def run_program(encoded, n_eff, tile_bits, params, state=None, reg_bits=4):
                         raise AssertionError(kind)
 
                     active = np.ones_like(e, dtype=bool) if po["ctrl_kind"] == K_NONE else bit_of(po["ctrl_kind"], po["ctrl_pos"]).astype(bool)
-                    if neg:  # negated control: the control = 0 half of a fused select pair
-                        assert po["ctrl_kind"] != K_NONE and kind == DENSE
-                        active = ~active
-                    if kind == DIAG:
+                    if po["kind"] == DIAG:
                         tb = bit_of(po["tgt_kind"], po["tgt_pos"])
                         factor = np.where(tb == 1, m[1, 1], m[0, 0])
                         tile = np.where(active, tile * factor, tile)

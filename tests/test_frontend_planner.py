@@ -248,60 +248,3 @@ def test_diagonal_energy_bitstring_evaluator_contract():
         ev.evaluate_bitstring("01a1")
     clone = pickle.loads(pickle.dumps(ev))
     assert clone.evaluate_bitstring("1010") == ev.evaluate_bitstring("1010")
-
-
-# ------------------------------------------------------------------------------------ phase deferral + select fusion
-def _probabilities(gates, values, k, r, low):
-    plan = sc.plan_circuit(gates.ops, gates.n_qubits, k, r, low)
-    enc = sc.encode_plan(plan)
-    state = run_program(enc, plan.n_eff, k, list(values), reg_bits=r)
-    return np.abs(state[: 1 << gates.n_qubits]) ** 2, plan
-
-
-@pytest.mark.parametrize("k,r,low", [(6, 4, 2), (8, 4, 4), (7, 3, 3), (sc.TILE_BITS, 4, 4)])
-@pytest.mark.parametrize("n,layers,seed", [(6, 4, 20), (9, 5, 21), (12, 4, 22)])
-def test_deferred_and_fused_plans_keep_the_probabilities(k, r, low, n, layers, seed):
-    """What the evaluators plan for diagonal observables / sampling (engine.rewritten: phase deferral, then select fusion in
-    plan_circuit): |psi_k|^2 must equal the oracle's, with the fused pairs landing on register-bit, thread-bit and external
-    controls (small tiles force all three), negated controls and bound matrix products included."""
-    from queasars_b200.engine import rewritten
-
-    genome, values = og.random_individual(n, layers, True, seed)
-    instr = og.individual_circuit(genome, values)
-    gates = rewritten(gl.from_circuit(build_circuit(instr, n)), drop_final_phases=True)
-    want = np.abs(oq.statevector(instr, n, values)) ** 2
-    got, plan = _probabilities(gates, values, k, r, low)
-    np.testing.assert_allclose(got, want, atol=1e-13)
-    negs = [po for s in plan.sweeps for p in s.passes for po in p.ops if po.neg]
-    if n >= 9:  # (the 6-qubit circuit has no rotation next to a controlled rotation on one target)
-        assert negs, "no select fusion happened"
-        assert any(plan.ops[po.op_index].mul_op != 0 for s in plan.sweeps for p in s.passes for po in p.ops)
-        assert len(plan.ops) > len(gates.ops)  # fused ops were appended to the op table, old indices stay valid
-    # the un-fused plan of the same gate list gives the same probabilities and costs more FP64 work
-    old = sc.FUSE_SELECTS
-    sc.FUSE_SELECTS = False
-    try:
-        plain, plan0 = _probabilities(gates, values, k, r, low)
-    finally:
-        sc.FUSE_SELECTS = old
-    np.testing.assert_allclose(plain, want, atol=1e-13)
-
-    def work(p):
-        return sum(gl.dfma_per_amplitude(p.ops[po.op_index]) for s in p.sweeps for ps in s.passes for po in ps.ops)
-
-    assert work(plan) <= work(plan0) and (not negs or work(plan) < work(plan0))
-
-
-def test_select_fusion_control_kinds_are_all_exercised():
-    """Across a few circuits and tile shapes the negated-control ops must have met every control kind the kernel implements."""
-    from queasars_b200.engine import rewritten
-
-    kinds = set()
-    for seed, (k, r, low) in enumerate([(6, 4, 2), (7, 4, 3), (8, 4, 4), (6, 3, 2)]):
-        genome, values = og.random_individual(10, 5, True, 40 + seed)
-        instr = og.individual_circuit(genome, values)
-        gates = rewritten(gl.from_circuit(build_circuit(instr, 10)), drop_final_phases=True)
-        got, plan = _probabilities(gates, values, k, r, low)
-        np.testing.assert_allclose(got, np.abs(oq.statevector(instr, 10, values)) ** 2, atol=1e-13)
-        kinds |= {po.ctrl_kind for s in plan.sweeps for p in s.passes for po in p.ops if po.neg}
-    assert kinds == {sc.K_REG, sc.K_THREAD, sc.K_EXT}
