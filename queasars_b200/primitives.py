@@ -174,6 +174,7 @@ class _B200Primitive:
         self._queue_obj: Optional[CoalescingQueue] = None
         self._pool_obj = None
         self._sharded_obj: dict = {}
+        self._shard_lock = threading.Lock()  # ONE sharded state per primitive: wide circuits are evaluated one at a time
         self._lock = threading.Lock()
         self._rr = 0  # round-robin start of the device choice for small submissions
 
@@ -444,13 +445,14 @@ class B200EstimatorV2(_B200Primitive):
             values.extend(vals)
         if self._needs_sharding(int(operator.num_qubits)):
             # one statevector over the whole device set, circuit after circuit (sharded.py): same values, no batch
-            sv = self._sharded_state(int(operator.num_qubits))
             flat = []
-            for circuit, vals in zip(circuits, values):
-                gates, bound = self._bound_gates(circuit, vals)
-                sv.reset()
-                sv.run(gates, bound)
-                flat.append(sv.expectation(operator))
+            with self._shard_lock:
+                sv = self._sharded_state(int(operator.num_qubits))
+                for circuit, vals in zip(circuits, values):
+                    gates, bound = self._bound_gates(circuit, vals)
+                    sv.reset()
+                    sv.run(gates, bound)
+                    flat.append(sv.expectation(operator))
             out, pos = [], 0
             for n in sizes:
                 out.append(np.asarray(flat[pos : pos + n], dtype=np.float64))
@@ -550,14 +552,15 @@ class B200SamplerV2(_B200Primitive):
             circuits.extend(circs)
             values.extend(vals)
         if self._needs_sharding(key[2]):
-            sv = self._sharded_state(key[2])
             rows = []
-            for circuit, vals in zip(circuits, values):
-                gates, bound = self._bound_gates(circuit, vals)
-                sv.reset()
-                sv.run(gates, bound)
-                rng = self.seed if isinstance(self.seed, np.random.Generator) else np.random.default_rng(self.seed)
-                rows.append(sv.sample(shots, uniforms=rng.random(shots)))
+            with self._shard_lock:
+                sv = self._sharded_state(key[2])
+                for circuit, vals in zip(circuits, values):
+                    gates, bound = self._bound_gates(circuit, vals)
+                    sv.reset()
+                    sv.run(gates, bound)
+                    rng = self.seed if isinstance(self.seed, np.random.Generator) else np.random.default_rng(self.seed)
+                    rows.append(sv.sample(shots, uniforms=rng.random(shots)))
             out, pos = [], 0
             for n in sizes:
                 out.append(np.stack(rows[pos : pos + n]))
