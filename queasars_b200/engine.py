@@ -367,6 +367,33 @@ class Engine:
         _native.check(self._lib.qb_evaluate_expectation(self._ctx, len(plans), _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), ham.ham_id, _native.ptr(out)))
         return out
 
+    def expectation_submit(self, plans: Sequence[PlanHandle], params: Sequence[Sequence[float]], ham: HamiltonianHandle) -> int:
+        """Queue the evaluation of a whole list on this engine's stream and return at once (``qb_evaluate_expectation_submit``);
+        ``expectation_collect`` waits for it.  A caller that drives several devices submits to all of them first and collects
+        afterwards, so the GPUs work concurrently without one Python thread per device.  The engine stays reserved for the
+        caller between the two calls (other submitters wait).  Raises ``QbError`` (``QB_ERR_MEMORY``) when the list does not
+        fit the statevector workspace in one piece -- use ``expectation`` then, which chunks by memory."""
+        if len(plans) != len(params):
+            raise ValueError(f"{len(plans)} circuits but {len(params)} parameter vectors")
+        ids, flat, offsets = self._pack(plans, params)
+        self._submit_lock.acquire()
+        try:
+            _native.check(self._lib.qb_evaluate_expectation_submit(self._ctx, len(plans), _native.ptr(ids), _native.ptr(flat), _native.ptr(offsets), ham.ham_id))
+        except BaseException:
+            self._lib.qb_evaluate_expectation_collect(self._ctx, 0, None)  # drain whatever was queued
+            self._submit_lock.release()
+            raise
+        return len(plans)
+
+    def expectation_collect(self, count: int) -> np.ndarray:
+        """Wait for the list queued by ``expectation_submit`` and return its ``count`` values in submission order."""
+        out = np.empty(count, dtype=np.float64)
+        try:
+            _native.check(self._lib.qb_evaluate_expectation_collect(self._ctx, count, _native.ptr(out)))
+        finally:
+            self._submit_lock.release()
+        return out
+
     def _pipeline_split(self, plans: Sequence[PlanHandle], params) -> Optional[int]:
         """Size of the first chunk of a two-chunk pipelined submission, or None to submit in one piece.  Worth it when the
         parameter values arrive as Python sequences (not arrays) and the batch is large; the split point is chosen so that

@@ -460,14 +460,57 @@ class B200EstimatorV2(_B200Primitive):
             return out
         fp = key[2]
         resolved = self._resolve_all(circuits, values, probabilities_only=self.hamiltonian_for(operator, fingerprint=fp).diagonal)
-        flat = self._run_per_device(
-            resolved, lambda slot, plans, params: self.engines[slot].expectation(plans, params, self.hamiltonian_for(operator, slot=slot, fingerprint=fp))
-        )
+        flat = self._expectation_on_devices(resolved, operator, fp)
         out, pos = [], 0
         for n in sizes:
             out.append(np.asarray(flat[pos : pos + n], dtype=np.float64))
             pos += n
         return out
+
+    def _expectation_on_devices(self, resolved, operator, fp) -> list:
+        """<H> of every resolved (slot, plan, values) entry, in submission order.  One device: one blocking native call.  Several
+        devices: the shares are queued on all devices first (non-blocking submit) and collected afterwards, so the GPUs work
+        concurrently and the host spends no time handing work to per-device Python threads; a share too large to queue in one
+        piece falls back to the blocking, memory-chunked call on a worker thread."""
+        by_slot: dict = {}
+        for i, (slot, _, _) in enumerate(resolved):
+            by_slot.setdefault(slot, []).append(i)
+        if len(by_slot) == 1:
+            return self._run_per_device(
+                resolved, lambda slot, plans, params: self.engines[slot].expectation(plans, params, self.hamiltonian_for(operator, slot=slot, fingerprint=fp))
+            )
+        results = [None] * len(resolved)
+        queued, blocking, error = [], [], None
+        for slot, rows in by_slot.items():
+            engine = self.engines[slot]
+            plans, params = [resolved[i][1] for i in rows], [resolved[i][2] for i in rows]
+            try:
+                ham = self.hamiltonian_for(operator, slot=slot, fingerprint=fp)
+                engine.expectation_submit(plans, params, ham)
+                queued.append((engine, rows))
+            except _native.QbError as exc:
+                if exc.code != _native.QB_ERR_MEMORY:
+                    error = error or exc
+                    break
+                blocking.append((self._pool.submit(engine.expectation, plans, params, ham), rows))
+            except BaseException as exc:  # noqa: BLE001 -- everything already queued must still be collected
+                error = error or exc
+                break
+        for engine, rows in queued:
+            try:
+                for i, r in zip(rows, engine.expectation_collect(len(rows))):
+                    results[i] = r
+            except BaseException as exc:  # noqa: BLE001
+                error = error or exc
+        for future, rows in blocking:
+            try:
+                for i, r in zip(rows, future.result()):
+                    results[i] = r
+            except BaseException as exc:  # noqa: BLE001
+                error = error or exc
+        if error is not None:
+            raise error
+        return results
 
     def _noisy(self, evs: np.ndarray, precision: float) -> np.ndarray:
         if not precision:

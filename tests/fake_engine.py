@@ -73,6 +73,15 @@ class FakeEngine:
             self.launch_count += 1
         return np.asarray(out)
 
+    def expectation_submit(self, plans, params, ham):
+        self._queued = self.expectation(plans, params, ham)
+        return len(plans)
+
+    def expectation_collect(self, count):
+        out, self._queued = self._queued, None
+        assert len(out) == count
+        return out
+
     def sample(self, plans, params, shots, uniforms):
         out = np.empty((len(plans), shots), dtype=np.int64)
         for i, (plan, vals) in enumerate(zip(plans, params)):
