@@ -125,7 +125,9 @@ def check(code: int):
 
 
 def ptr(arr: np.ndarray):
-    return arr.ctypes.data_as(c_void_p)
+    """Address of the array's buffer (the c_void_p argtypes take a plain int: half the cost of ``ctypes.data_as``, which matters
+    on the single-circuit call path).  The caller keeps the array alive across the native call."""
+    return arr.ctypes.data
 
 
 def device_count() -> int:

@@ -20,7 +20,7 @@ class _Slot:
 
     def __init__(self, key: Hashable, payload: Any):
         self.key, self.payload = key, payload
-        self.event = threading.Event()
+        self.event = None  # created only for requests that have to wait (a leader never waits on its own slot)
         self.promoted = False
         self.value = None
         self.error = None
@@ -40,10 +40,12 @@ class CoalescingQueue:
     def submit(self, key: Hashable, payload: Any) -> Any:
         slot = _Slot(key, payload)
         with self._lock:
-            self._pending.append(slot)
             leader = not self._busy
             if leader:
                 self._busy = True
+            else:
+                slot.event = threading.Event()
+            self._pending.append(slot)
         if not leader:
             slot.event.wait()
             if not slot.promoted:
@@ -80,7 +82,7 @@ class CoalescingQueue:
             self.batches_executed += 1
             self.requests_executed += len(slots)
         for s in batch:
-            if not s.promoted:
+            if s.event is not None and not s.promoted:
                 s.event.set()
 
     @staticmethod

@@ -300,6 +300,19 @@ class Engine:
     def _pack(plans: Sequence[PlanHandle], params: Sequence[Sequence[float]]):
         if len(plans) != len(params):
             raise ValueError(f"{len(plans)} circuits but {len(params)} parameter vectors")
+        if len(plans) == 1:  # the optimizer loop's call: one circuit, one parameter vector
+            row, want = params[0], plans[0].n_params
+            helper = _native.pyhelper() if isinstance(row, (list, tuple)) and len(row) == want and want else None
+            flat = None
+            if helper:
+                flat = np.empty(want, dtype=np.float64)
+                if helper.qb_pack_rows((row,), flat.ctypes.data, np.array([want], dtype=np.int64).ctypes.data, 1) != want:
+                    flat = None
+            if flat is None:
+                flat = np.asarray(row, dtype=np.float64).reshape(-1)
+            if flat.size != want:
+                raise ValueError(f"circuit 0 has {want} parameters but {flat.size} values were given")
+            return np.array([plans[0].plan_id], dtype=np.int64), (flat if flat.size else np.zeros(1, dtype=np.float64)), np.array([0, flat.size], dtype=np.int64)
         ids = np.fromiter((p.plan_id for p in plans), dtype=np.int64, count=len(plans))
         offsets = np.zeros(len(plans) + 1, dtype=np.int64)
         if isinstance(params, np.ndarray) and params.ndim == 2 and params.dtype == np.float64:
