@@ -434,6 +434,7 @@ def run_b200(args):
             line["c4_26q_sampler"] = guarded(lambda: c4_probe(local_rank))
             line["e2e_threaded"] = guarded(lambda: threaded_probe(local_rank, operator, circuits, params, values, args))
             line["c1_jssp_reference_loop"] = guarded(lambda: c1_probe(local_rank))
+            line["c2_complex64"] = guarded(lambda: complex64_probe(local_rank, operator, circuits, params, values, args))
         else:
             line["strong"] = guarded(lambda: strong_probe(dist, rank, world, engine, plans, ham, params, values, args, barrier, max_over_ranks))
             batch.close()
@@ -645,6 +646,24 @@ def c1_probe(device):
         out[which] = {"objective": float(result.eigenvalue), "notebook_value": best, "circuit_evaluations": evals, "seconds": dt, "evals_per_s": evals / dt,
                       "generations": len(result.circuit_evaluations)}
     return out
+
+
+def complex64_probe(device, operator, circuits, params, values, args):
+    """The optional complex64 path on the headline workload (same population, same Hamiltonian): end-to-end evals/s through the
+    evaluator and the error against the complex128 values (north star: 1e-4 relative in fp32).  Not the headline: BASELINE's metric
+    is complex128."""
+    from queasars_b200 import B200EstimatorV2, B200OperatorCircuitEvaluator
+
+    est = B200EstimatorV2(device=device, dtype="complex64", coalesce=False)
+    ev = B200OperatorCircuitEvaluator(est, 0.0, operator)
+    got = ev.evaluate_circuits(circuits, params)
+    err = float(np.max(np.abs(np.asarray(got) - np.asarray(values)) / np.maximum(1.0, np.abs(values))))
+    reps = max(10, min(args.steps, 100))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ev.evaluate_circuits(circuits, params)
+    dt = time.perf_counter() - t0
+    return {"evals_per_s": POPULATION * reps / dt, "ms_per_call": 1e3 * dt / reps, "max_rel_err_vs_complex128": err, "tolerance": 1e-4}
 
 
 def threaded_probe(device, operator, circuits, params, values, args):
