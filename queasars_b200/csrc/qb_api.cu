@@ -174,7 +174,7 @@ struct qb_context {
     cudaStream_t aux_streams[8] = {};
     cudaEvent_t fork_event = nullptr, join_events[8] = {};
     bool force_idx64 = false;  // qb_context_set_index_width(64): run the 64-bit-index sweep kernels at any size (tests)
-    int tiles_log2 = -1;  // tiles per sweep CTA (log2); -1 = by size (4 tiles, 8 from 2^13 tiles per state on); QB_TILES_LOG2 overrides
+    int tiles_log2 = -1;  // tiles per sweep CTA (log2); -1 = 8 tiles, fewer while a launch would not fill two waves of CTAs; QB_TILES_LOG2 overrides
     std::mutex mu;
     std::map<int64_t, std::unique_ptr<Plan>> plans;
     std::map<int64_t, std::unique_ptr<Ham>> hams;
@@ -309,7 +309,10 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
     b.fuse_expect = ham && ham->table.p && ham->table_n_eff == b.n_eff && index_offset == 0;  // diagonal part in the last sweep
     b.skip_final_store = b.fuse_expect && ham->diagonal && !external_state;
     b.n_tiles = size_t(1) << (b.n_eff - b.tile_bits);
-    b.tiles_log2 = std::min(ctx->tiles_log2 >= 0 ? ctx->tiles_log2 : (b.n_eff - b.tile_bits >= 13 ? 3 : 2), b.n_eff - b.tile_bits);
+    // 8 tiles per CTA: the staging of the sweep program (pass records, matrices, slot tables: ~8 % of the warp time at 4 tiles) is
+    // paid once per 8 tiles; with the sweep launches overlapping as stream groups the longer CTAs no longer cost a tail
+    // (measured on the bench workload: 1 / 2 / 4 / 8 / 16 tiles per CTA -> 25.3 / 28.9 / 31.3 / 32.2 / 30.5 k evals/s)
+    b.tiles_log2 = std::min(ctx->tiles_log2 >= 0 ? ctx->tiles_log2 : 3, b.n_eff - b.tile_bits);
     if (ctx->tiles_log2 < 0) {  // small batches: rather more CTAs than amortised staging -- keep at least two waves of them
         const size_t slots = size_t(ctx->sm_count) * (b.tile_bits <= 11 ? 4 : 2);
         while (b.tiles_log2 > 0 && ((b.n_tiles * size_t(batch)) >> b.tiles_log2) < 2 * slots) --b.tiles_log2;

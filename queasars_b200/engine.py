@@ -131,7 +131,7 @@ def pipeline_split_point(n: int, n_eff: int, tile_bits: int, sm_count: int) -> O
     if n < 8 or n_eff > 24:
         return None
     tiles = 1 << (n_eff - tile_bits)
-    ctas = max(1, tiles >> min(3 if n_eff - tile_bits >= 13 else 2, n_eff - tile_bits))
+    ctas = max(1, tiles >> min(3, n_eff - tile_bits))
     slots = sm_count * (4 if tile_bits <= 11 else 2)
 
     def waste(c: int) -> float:
