@@ -215,11 +215,12 @@ def test_planner_invariants():
 
 
 def test_pipeline_split_point_fills_whole_waves():
-    """Host logic of the pipelined submission (engine.pipeline_split_point): 32 twenty-qubit evaluations on 148 SMs are cut
-    into 9 + 23 (1.95 and 4.97 waves of 592 resident sweep CTAs); small lists and large states are not split."""
+    """Host logic of the pipelined submission (engine.pipeline_split_point; used on the NumPy conversion path only): 32
+    twenty-qubit evaluations on 148 SMs (64 sweep CTAs per state at 8 tiles per CTA, 592 resident) are cut into 6 + 26 (the
+    second chunk fills 2.81 waves); small lists and large states are not split."""
     from queasars_b200.engine import pipeline_split_point
 
-    assert pipeline_split_point(32, 20, 11, 148) == 9
+    assert pipeline_split_point(32, 20, 11, 148) == 6
     assert pipeline_split_point(7, 20, 11, 148) is None
     assert pipeline_split_point(32, 26, 11, 148) is None
     for n in (8, 16, 24, 40, 64):
