@@ -173,6 +173,16 @@ int qb_sample(qb_context* ctx, int batch, const int64_t* plan_ids,
 int qb_statevector(qb_context* ctx, int64_t plan_id, const double* params, int n_params,
                    double* out_re_im /* 2 * 2^n doubles */);
 
+/* One evaluate_circuits() list split over several GPUs of one process (the device sets of queasars_b200/primitives.py: the
+ * reference wraps ONE primitive in a ThreadPoolExecutor, evqe.py:232-236): entry i of every array belongs to context ctxs[i] and
+ * has the meaning of the corresponding qb_evaluate_expectation argument.  Every context evaluates its share on its own host
+ * thread (created on first use, owned by the context), so the devices are fed concurrently and outside a Python caller's
+ * interpreter lock; returns when all shares are done.  A context may appear once per call; concurrent calls on disjoint
+ * context sets are fine, calls that share a context are serialised by the caller. */
+int qb_evaluate_expectation_multi(int n_ctx, qb_context* const* ctxs, const int* batches, const int64_t* const* plan_ids,
+                                  const double* const* params, const int64_t* const* param_offsets, const int64_t* ham_ids,
+                                  double* const* out_values);
+
 /* Pipelined form of qb_evaluate_expectation for one evaluate_circuits() list handed over in chunks: _submit queues a chunk
  * (upload, kernels, download into a pinned buffer) and returns without waiting, so the caller can prepare the next chunk's
  * parameter values (in QUEASARS: Python lists of floats, circuit_evaluation.py:205-207) while the GPU works; _collect waits

@@ -47,6 +47,7 @@ def _declare(lib):
         "qb_hamiltonian_destroy": [c_void_p, c_int64],
         "qb_hamiltonian_diag_energies": [c_void_p, c_int64, c_int64, c_void_p, c_void_p],
         "qb_evaluate_expectation": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
+        "qb_evaluate_expectation_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
         "qb_evaluate_expectation_submit": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64],
         "qb_evaluate_expectation_collect": [c_void_p, c_int, c_void_p],
         "qb_context_sm_count": [c_void_p],
@@ -90,7 +91,7 @@ EXPORTED_SYMBOLS = (
     "qb_device_count qb_context_create qb_context_destroy qb_last_error qb_context_stream qb_context_launch_count "
     "qb_context_set_workspace_limit qb_context_workspace qb_context_synchronize qb_context_set_index_width qb_plan_create qb_plan_destroy qb_plan_set_prefix qb_hamiltonian_create "
     "qb_hamiltonian_destroy qb_hamiltonian_diag_energies qb_evaluate_expectation qb_sample qb_statevector "
-    "qb_evaluate_expectation_submit qb_evaluate_expectation_collect qb_context_sm_count "
+    "qb_evaluate_expectation_multi qb_evaluate_expectation_submit qb_evaluate_expectation_collect qb_context_sm_count "
     "qb_batch_create qb_batch_set_params qb_batch_run qb_batch_run_timed qb_batch_read qb_batch_destroy qb_batch_stats "
     "qb_apply_plan_device qb_expectation_device qb_sample_device qb_swap_global_p2p qb_record_sizes "
     "qb_device_alloc qb_device_free qb_device_read qb_enable_peer_access qb_ipc_export qb_ipc_open qb_ipc_close"

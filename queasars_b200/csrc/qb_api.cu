@@ -1,14 +1,17 @@
 // C-ABI implementation (include/queasars_b200.h): contexts, plans, Hamiltonians, batched evaluation.
 // No CPU fallback: every compute entry point needs a CUDA device and fails with QB_ERR_CUDA otherwise.
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "qb_kernels.cuh"
@@ -142,6 +145,54 @@ struct DeviceBatch {
     }
 };
 
+// One host thread per context for qb_evaluate_expectation_multi: a caller that drives several GPUs hands every context its share
+// and all of them build, launch and wait concurrently -- outside the interpreter lock of a Python caller, which is what makes a
+// single process able to keep several GPUs busy with small shares.
+struct Worker {
+    std::thread thread;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> task;
+    bool has_task = false, done = false, stop = false;
+    int rc = QB_OK;
+    std::string error;
+
+    void loop() {
+        std::unique_lock<std::mutex> lock(m);
+        for (;;) {
+            cv.wait(lock, [&] { return has_task || stop; });
+            if (stop) return;
+            std::function<int()> fn = std::move(task);
+            has_task = false;
+            lock.unlock();
+            const int r = fn();
+            std::string msg = r == QB_OK ? std::string() : g_last_error;  // (thread-local: this thread's)
+            lock.lock();
+            rc = r, error = std::move(msg), done = true;
+            cv.notify_all();
+        }
+    }
+    void post(std::function<int()> fn) {
+        std::lock_guard<std::mutex> lock(m);
+        task = std::move(fn), has_task = true, done = false;
+        cv.notify_all();
+    }
+    int wait(std::string& msg) {
+        std::unique_lock<std::mutex> lock(m);
+        cv.wait(lock, [&] { return done; });
+        msg = error;
+        return rc;
+    }
+    ~Worker() {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            stop = true;
+            cv.notify_all();
+        }
+        if (thread.joinable()) thread.join();
+    }
+};
+
 // One (plan, Hamiltonian) evaluation captured as a CUDA graph: parameter upload from a fixed pinned buffer, bind, sweeps,
 // expectation, result download into a fixed pinned buffer.  Replayed by the single-circuit calls of an optimizer loop
 // (mutation.py:63-75 re-submits ONE circuit with new parameter values), where launch latency, not the GPU, sets the pace.
@@ -197,6 +248,8 @@ struct qb_context {
     std::map<std::pair<int64_t, int64_t>, std::unique_ptr<SingleGraph>> single_graphs;
     size_t single_graph_bytes = 0;
     uint64_t use_clock = 0;
+    std::unique_ptr<Worker> worker;  // created by the first qb_evaluate_expectation_multi that includes this context
+    std::mutex worker_mu;
 };
 
 namespace {
@@ -766,6 +819,7 @@ int qb_context_create(int device, void* stream, qb_context** out) {
 
 int qb_context_destroy(qb_context* ctx) {
     if (!ctx) return QB_OK;
+    ctx->worker.reset();  // stops and joins the context's host thread
     DeviceScope scope(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->single_graphs.clear();
@@ -1474,6 +1528,47 @@ int qb_evaluate_expectation_collect(qb_context* ctx, int total, double* out_valu
     for (const auto& ch : chunks)
         for (size_t pos = 0; pos < ch.order.size(); ++pos) out_values[ch.offset + size_t(ch.order[pos])] = res[ch.offset + pos];
     return QB_OK;
+}
+
+int qb_evaluate_expectation_multi(int n_ctx, qb_context* const* ctxs, const int* batches, const int64_t* const* plan_ids,
+                                  const double* const* params, const int64_t* const* param_offsets, const int64_t* ham_ids,
+                                  double* const* out_values) {
+    if (n_ctx < 0 || (n_ctx > 0 && (!ctxs || !batches || !plan_ids || !params || !param_offsets || !ham_ids || !out_values)))
+        return fail(QB_ERR_INVALID, "null argument");
+    for (int i = 0; i < n_ctx; ++i) {
+        if (!ctxs[i]) return fail(QB_ERR_INVALID, "null context");
+        for (int j = 0; j < i; ++j)
+            if (ctxs[j] == ctxs[i]) return fail(QB_ERR_INVALID, "a context may appear once per call");
+    }
+    std::vector<Worker*> posted;
+    for (int i = 0; i < n_ctx; ++i) {
+        if (batches[i] <= 0) continue;
+        qb_context* ctx = ctxs[i];
+        {
+            std::lock_guard<std::mutex> lock(ctx->worker_mu);
+            if (!ctx->worker) {
+                ctx->worker = std::make_unique<Worker>();
+                Worker* w = ctx->worker.get();
+                w->thread = std::thread([w] { w->loop(); });
+            }
+        }
+        const int batch = batches[i];
+        const int64_t* ids = plan_ids[i];
+        const double* vals = params[i];
+        const int64_t* offs = param_offsets[i];
+        const int64_t ham = ham_ids[i];
+        double* out = out_values[i];
+        ctx->worker->post([=] { return qb_evaluate_expectation(ctx, batch, ids, vals, offs, ham, out); });
+        posted.push_back(ctx->worker.get());
+    }
+    int rc = QB_OK;
+    std::string first;
+    for (Worker* w : posted) {  // wait for every device before reporting the first failure
+        std::string msg;
+        const int r = w->wait(msg);
+        if (r != QB_OK && rc == QB_OK) rc = r, first = msg;
+    }
+    return rc == QB_OK ? QB_OK : fail(rc, first);
 }
 
 int qb_context_sm_count(qb_context* ctx) { return ctx ? ctx->sm_count : 0; }

@@ -17,6 +17,7 @@ accepted and produce array-shaped ``evs`` / one register per row.
 """
 from __future__ import annotations
 
+import ctypes
 import threading
 import weakref
 from typing import Iterable, Optional, Sequence
@@ -469,9 +470,8 @@ class B200EstimatorV2(_B200Primitive):
 
     def _expectation_on_devices(self, resolved, operator, fp) -> list:
         """<H> of every resolved (slot, plan, values) entry, in submission order.  One device: one blocking native call.  Several
-        devices: the shares are queued on all devices first (non-blocking submit) and collected afterwards, so the GPUs work
-        concurrently and the host spends no time handing work to per-device Python threads; a share too large to queue in one
-        piece falls back to the blocking, memory-chunked call on a worker thread."""
+        devices: the shares are packed here and handed to ONE native call that evaluates every device's share on that context's
+        own host thread, so the GPUs are fed concurrently without per-device Python threads."""
         by_slot: dict = {}
         for i, (slot, _, _) in enumerate(resolved):
             by_slot.setdefault(slot, []).append(i)
@@ -480,36 +480,38 @@ class B200EstimatorV2(_B200Primitive):
                 resolved, lambda slot, plans, params: self.engines[slot].expectation(plans, params, self.hamiltonian_for(operator, slot=slot, fingerprint=fp))
             )
         results = [None] * len(resolved)
-        queued, blocking, error = [], [], None
-        for slot, rows in by_slot.items():
+        shares = []
+        for slot, rows in sorted(by_slot.items()):
             engine = self.engines[slot]
-            plans, params = [resolved[i][1] for i in rows], [resolved[i][2] for i in rows]
-            try:
-                ham = self.hamiltonian_for(operator, slot=slot, fingerprint=fp)
-                engine.expectation_submit(plans, params, ham)
-                queued.append((engine, rows))
-            except _native.QbError as exc:
-                if exc.code != _native.QB_ERR_MEMORY:
-                    error = error or exc
-                    break
-                blocking.append((self._pool.submit(engine.expectation, plans, params, ham), rows))
-            except BaseException as exc:  # noqa: BLE001 -- everything already queued must still be collected
-                error = error or exc
-                break
-        for engine, rows in queued:
-            try:
-                for i, r in zip(rows, engine.expectation_collect(len(rows))):
+            ids, flat, offsets = Engine._pack([resolved[i][1] for i in rows], [resolved[i][2] for i in rows])
+            shares.append((engine, rows, ids, flat, offsets, np.empty(len(rows), dtype=np.float64), self.hamiltonian_for(operator, slot=slot, fingerprint=fp)))
+        if not all(hasattr(sh[0], "_ctx") for sh in shares):  # (test doubles without a native context: one blocking call per device)
+            for engine, rows, *_rest, ham in shares:
+                for i, r in zip(rows, engine.expectation([resolved[i][1] for i in rows], [resolved[i][2] for i in rows], ham)):
                     results[i] = r
-            except BaseException as exc:  # noqa: BLE001
-                error = error or exc
-        for future, rows in blocking:
-            try:
-                for i, r in zip(rows, future.result()):
-                    results[i] = r
-            except BaseException as exc:  # noqa: BLE001
-                error = error or exc
-        if error is not None:
-            raise error
+            return results
+        n = len(shares)
+        lib = shares[0][0]._lib
+        ctxs = (ctypes.c_void_p * n)(*[sh[0]._ctx.value for sh in shares])
+        batches = (ctypes.c_int * n)(*[len(sh[1]) for sh in shares])
+        ids_p = (ctypes.c_void_p * n)(*[sh[2].ctypes.data for sh in shares])
+        vals_p = (ctypes.c_void_p * n)(*[sh[3].ctypes.data for sh in shares])
+        offs_p = (ctypes.c_void_p * n)(*[sh[4].ctypes.data for sh in shares])
+        outs_p = (ctypes.c_void_p * n)(*[sh[5].ctypes.data for sh in shares])
+        hams = (ctypes.c_int64 * n)(*[sh[6].ham_id for sh in shares])
+        # ONE native call: every context evaluates its share on its own host thread (qb_evaluate_expectation_multi), outside the
+        # interpreter lock.  A context serves one such call at a time: the engines' submit locks are taken in device order.
+        locks = [sh[0]._submit_lock for sh in sorted(shares, key=lambda sh: sh[0].device)]
+        for lock in locks:
+            lock.acquire()
+        try:
+            _native.check(lib.qb_evaluate_expectation_multi(n, ctxs, batches, ids_p, vals_p, offs_p, hams, outs_p))
+        finally:
+            for lock in reversed(locks):
+                lock.release()
+        for _, rows, _ids, _flat, _offs, out, _ham in shares:
+            for i, r in zip(rows, out):
+                results[i] = r
         return results
 
     def _noisy(self, evs: np.ndarray, precision: float) -> np.ndarray:
