@@ -825,6 +825,7 @@ def sharded_probe(dist, rank, world, local_rank):
     tf = sv.expectation(gn.tfim_operator(n))
     entry = {"n_qubits": n, "swaps": sv.swaps_done, "swap_path": "p2p kernel (peer memory)" if sv._peer_ptrs is not None else "nccl all_to_all",
              "swap_fallback_reason": getattr(sv, "swap_fallback_reason", None)}
+    sv.close()  # collective: unmap the peers' buffers before anyone frees its own
     del sv
     torch.cuda.empty_cache()
     if rank == 0:
@@ -893,6 +894,7 @@ def sharded_probe(dist, rank, world, local_rank):
         "swap_path": "swap_p2p_kernel: one fused kernel (peer stores over NVLink) + barrier" if sv._peer_ptrs is not None else "pack + all_to_all_single + unpack",
         "swap_fallback_reason": getattr(sv, "swap_fallback_reason", None),
     }
+    sv.close()
     del sv
     torch.cuda.empty_cache()
     return out

@@ -134,5 +134,6 @@ if rank == 0:
         out["tfim_rel_err"] = abs(tfim_value - tref) / max(1.0, abs(tref))
         out["sampled_vs_exact_energy"] = [sampled_energy, float(ref)]
     print(json.dumps(out))
+sv.close()
 if world > 1:
     dist.destroy_process_group()
