@@ -56,6 +56,8 @@ class CoalescingQueue:
         try:
             self._run(batch)
         finally:
+            # hand the engine on BEFORE waking this batch's callers: the next leader then starts preparing its batch while the
+            # finished callers are still being woken (they all need the interpreter lock to return), not after them
             with self._lock:
                 if self._pending:
                     nxt = self._pending[0]
@@ -63,6 +65,9 @@ class CoalescingQueue:
                     nxt.event.set()
                 else:
                     self._busy = False
+            for s in batch:
+                if s.event is not None and s is not slot:
+                    s.event.set()
         return self._finish(slot)
 
     def _run(self, batch: list[_Slot]) -> None:
@@ -81,9 +86,6 @@ class CoalescingQueue:
                     s.error = exc
             self.batches_executed += 1
             self.requests_executed += len(slots)
-        for s in batch:
-            if s.event is not None and not s.promoted:
-                s.event.set()
 
     @staticmethod
     def _finish(slot: _Slot):
