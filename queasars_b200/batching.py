@@ -56,8 +56,12 @@ class CoalescingQueue:
         try:
             self._run(batch)
         finally:
-            # hand the engine on BEFORE waking this batch's callers: the next leader then starts preparing its batch while the
-            # finished callers are still being woken (they all need the interpreter lock to return), not after them
+            # wake this batch's callers first, then hand the engine on: the callers re-submit while the next leader is being
+            # woken, so its batch is fuller (promoting first was measured slower and more erratic: 5-14 k vs 13-16 k evals/s
+            # with 32 threads on the bench workload)
+            for s in batch:
+                if s.event is not None and s is not slot:
+                    s.event.set()
             with self._lock:
                 if self._pending:
                     nxt = self._pending[0]
@@ -65,9 +69,6 @@ class CoalescingQueue:
                     nxt.event.set()
                 else:
                     self._busy = False
-            for s in batch:
-                if s.event is not None and s is not slot:
-                    s.event.set()
         return self._finish(slot)
 
     def _run(self, batch: list[_Slot]) -> None:
