@@ -90,6 +90,7 @@ def jssp_4q(ref):
 
 JSSP_INSTANCES = {
     # name: (jobs as ((machine, duration), ...), makespan_limit, n_qubits, notebook convergence value = minimum diagonal energy)
+    # (second-lowest energies, SURVEY.md section 8c-2: 338.5 / 92.4 / 52.125)
     "4q": (((("m0", 1), ("m1", 1)), (("m0", 1), ("m1", 1))), 3, 4, 63.5),  # evqe_jssp_small_examples.ipynb cells 4, 8, 14
     "5q": (((("m0", 1), ("m1", 2)), (("m0", 1), ("m1", 1), ("m2", 1))), 4, 5, 61.6),  # same notebook, cells 23, 27, 33
     "8q": (((("m0", 2), ("m1", 1)), (("m0", 1), ("m1", 2))), 5, 8, 22.75),  # using_the_ibm_runtime.ipynb cells 2, 6, 8
@@ -144,6 +145,9 @@ def jssp_solver(ref, sampler, executor, random_seed=0):
         mutually_exclusive_primitives=False,
     )
     return ref["EVQEMinimumEigensolver"](configuration=configuration)
+
+
+JSSP_SECOND_LEVEL = {"4q": 338.5, "5q": 92.4, "8q": 52.125}
 
 
 def likeliest_bitstring(result) -> str:
