@@ -11,7 +11,12 @@ from queasars_b200.schedule import K_EXT, K_NONE, K_REG, K_THREAD
 
 
 def op_matrix(angle_rec, params):
-    vals = [angle_rec["const"][j] + (angle_rec["coeff"][j] * params[angle_rec["slot"][j]] if angle_rec["slot"][j] >= 0 else 0.0) for j in range(4)]
+    vals = [
+        angle_rec["const"][j]
+        + (angle_rec["coeff"][j] * params[angle_rec["slot"][j]] if angle_rec["slot"][j] >= 0 else 0.0)
+        + (angle_rec["coeff2"][j] * params[angle_rec["slot2"][j]] if angle_rec["slot2"][j] >= 0 else 0.0)  # deferred phase of the previous gate
+        for j in range(4)
+    ]
     g, t, p, l = vals
     if angle_rec["kind"] == DIAG:
         return np.array([[cmath.exp(1j * g), 0], [0, cmath.exp(1j * (g + l))]])

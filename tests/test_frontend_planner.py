@@ -249,3 +249,77 @@ def test_diagonal_energy_bitstring_evaluator_contract():
         ev.evaluate_bitstring("01a1")
     clone = pickle.loads(pickle.dumps(ev))
     assert clone.evaluate_bitstring("1010") == ev.evaluate_bitstring("1010")
+
+
+# ------------------------------------------------------------------------------------ phase deferral (gate_list.defer_phases)
+def _apply_ops(ops, n, params):
+    state = np.zeros(1 << n, dtype=complex)
+    state[0] = 1.0
+    for op in ops:
+        m = np.array(op.matrix(params))
+        if op.control < 0:
+            state = oq.apply_matrix(state, n, m, [op.target])
+        else:
+            cm = np.kron(np.eye(2), np.diag([1, 0])) + np.kron(m, np.diag([0, 1]))
+            state = oq.apply_matrix(state, n, cm, [op.control, op.target])
+    return state
+
+
+def test_phase_deferral_is_exact_on_random_op_lists():
+    """u = D(phi) R_Y(theta) D(lam): deferring the trailing D(phi) of every uncontrolled gate (absorbed by the next gate on the
+    qubit, passed through controlled gates, re-applied at the end) leaves the state unchanged; dropping the final phases leaves
+    |psi_k|^2 unchanged; every uncontrolled dense gate ends up with phi == 0 (a real first column); angles stay affine in at
+    most two parameters."""
+    import random
+
+    rng = random.Random(3)
+    n, n_params = 5, 12
+
+    def angle():
+        return gl.Angle(rng.randrange(n_params), rng.uniform(-2, 2), rng.uniform(-3, 3)) if rng.random() < 0.7 else gl.const(rng.uniform(-3, 3))
+
+    for _ in range(40):
+        ops = []
+        for _ in range(25):
+            kind = rng.random()
+            t = rng.randrange(n)
+            c = rng.choice([q for q in range(n) if q != t])
+            gamma = gl.ZERO if rng.random() < 0.8 else angle()
+            if kind < 0.45:
+                ops.append(gl.KernelOp(gl.DENSE, t, -1, gamma, angle(), angle(), angle()))
+            elif kind < 0.8:
+                ops.append(gl.KernelOp(gl.DENSE, t, c, gamma, angle(), angle(), angle()))
+            elif kind < 0.9:
+                ops.append(gl.KernelOp(gl.DIAG, t, -1, angle(), gl.ZERO, gl.ZERO, angle()))
+            else:
+                ops.append(gl.KernelOp(gl.DIAG, t, c, angle(), gl.ZERO, gl.ZERO, angle()))
+        params = [rng.uniform(0, 6.28) for _ in range(n_params)]
+        want = _apply_ops(ops, n, params)
+        kept = gl.defer_phases(ops)
+        dropped = gl.defer_phases(ops, drop_final=True)
+        np.testing.assert_allclose(_apply_ops(kept, n, params), want, atol=1e-13)
+        np.testing.assert_allclose(np.abs(_apply_ops(dropped, n, params)) ** 2, np.abs(want) ** 2, atol=1e-13)
+        assert all(op.phi.is_zero for op in dropped if op.kind == gl.DENSE and op.control < 0)
+        assert len(dropped) <= len(ops) <= len(kept)
+
+
+@pytest.mark.parametrize("k,r,low", [(6, 4, 2), (8, 4, 4), (7, 3, 3), (sc.TILE_BITS, 4, 4)])
+@pytest.mark.parametrize("n,layers,seed", [(6, 4, 20), (9, 5, 21), (12, 4, 22)])
+def test_deferred_plans_keep_the_probabilities(k, r, low, n, layers, seed):
+    """What the evaluators plan for diagonal observables / sampling (engine.rewritten with drop_final_phases): the planned and
+    encoded program (two-term affine angles, qb_op_angles.slot2 / coeff2) must reproduce the oracle's |psi_k|^2 in the plan
+    emulator; without the flag the gate list is left as written."""
+    from queasars_b200.engine import rewritten
+
+    genome, values = og.random_individual(n, layers, True, seed)
+    instr = og.individual_circuit(genome, values)
+    gates = gl.from_circuit(build_circuit(instr, n))
+    assert rewritten(gates, drop_final_phases=False) is gates
+    deferred = rewritten(gates, drop_final_phases=True)
+    assert any(a.slot2 >= 0 for op in deferred.ops for a in op.angles)  # some gate absorbed a parameterised phase
+    want = np.abs(oq.statevector(instr, n, values)) ** 2
+    got, plan = emulate(deferred, values, k, r, low)
+    np.testing.assert_allclose(np.abs(got) ** 2, want, atol=1e-13)
+    from queasars_b200.gate_list import dfma_per_amplitude
+
+    assert sum(dfma_per_amplitude(op) for op in deferred.ops) < sum(dfma_per_amplitude(op) for op in gates.ops)
