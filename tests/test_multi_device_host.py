@@ -105,3 +105,36 @@ def test_fingerprints_detect_in_place_edits():
     fp = pr._operator_fingerprint(op)
     op._c[1] = 0.25 + 0j
     assert pr._operator_fingerprint(op) != fp
+
+
+def test_duplicate_pauli_terms_are_merged_in_first_appearance_order():
+    """engine.merge_duplicate_terms: the reference's JSSP encoder emits every (x, z) string several times over
+    (domain_wall_hamiltonian_encoder.py:189-230: 346 raw terms for 84 distinct strings at 26 qubits)."""
+    from queasars_b200.engine import merge_duplicate_terms
+
+    x = [0, 0, 5, 0, 5, 0, 5]
+    z = [3, 9, 1, 3, 1, 12, 2]
+    c = [1.0, 2.0, 3.0 + 1j, 4.0, 5.0, 6.0, 7.0]
+    mx, mz, mc = merge_duplicate_terms(x, z, c)
+    assert list(mx) == [0, 0, 5, 0, 5] and list(mz) == [3, 9, 1, 12, 2]
+    np.testing.assert_allclose(mc, [5.0, 2.0, 8.0 + 1j, 6.0, 7.0])
+    ux, uz, uc = merge_duplicate_terms([1, 2], [0, 0], [1.0, 2.0])
+    assert list(ux) == [1, 2] and list(uc) == [1.0, 2.0]
+
+
+def test_golden_jssp_hamiltonian_merges_to_its_distinct_terms(jssp_golden):
+    from queasars_b200.engine import merge_duplicate_terms
+
+    entry = jssp_golden["jssp_26q"]
+    z = np.asarray(entry["z_masks"], dtype=np.uint64)
+    c = np.asarray(entry["coeffs"], dtype=float)
+    x, mz, mc = merge_duplicate_terms(np.zeros_like(z), np.concatenate([z, z[:40]]), np.concatenate([c, c[:40]]))
+    assert len(mz) == len(set(int(v) for v in z))
+    probe = np.asarray(entry["probe_states"], dtype=np.uint64)
+
+    def energy(zz, cc, k):
+        return sum(float(np.real(cf)) * (1 - 2 * (bin(int(k) & int(zm)).count("1") & 1)) for zm, cf in zip(zz, cc))
+
+    for k, want in zip(probe, entry["probe_energies"]):
+        extra = energy(z[:40], c[:40], k)
+        assert energy(mz, mc, k) == pytest.approx(want + extra, rel=1e-12)
