@@ -128,7 +128,8 @@ def test_golden_jssp_hamiltonian_merges_to_its_distinct_terms(jssp_golden):
     entry = jssp_golden["jssp_26q"]
     z = np.asarray(entry["z_masks"], dtype=np.uint64)
     c = np.asarray(entry["coeffs"], dtype=float)
-    x, mz, mc = merge_duplicate_terms(np.zeros_like(z), np.concatenate([z, z[:40]]), np.concatenate([c, c[:40]]))
+    zz, cc = np.concatenate([z, z[:40]]), np.concatenate([c, c[:40]])
+    x, mz, mc = merge_duplicate_terms(np.zeros_like(zz), zz, cc)
     assert len(mz) == len(set(int(v) for v in z))
     probe = np.asarray(entry["probe_states"], dtype=np.uint64)
 
