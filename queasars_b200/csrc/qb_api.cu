@@ -132,6 +132,10 @@ struct DeviceBatch {
     std::vector<int64_t> param_begin;  // per caller index, offset into the params buffer
     int64_t total_params = 0, total_ops = 0;
     const Ham* ham = nullptr;
+    // what the buffers were last assembled for: an identical request (same plans, Hamiltonian, start) re-uses them as they are
+    std::vector<int64_t> built_ids;
+    uint64_t built_epoch = 0, built_offset = 0;
+    int built_init_zero = -1;
     bool fuse_expect = false;
     bool skip_final_store = false;  // fused diagonal <H> is the whole result: the last sweep does not write the state back
     size_t n_tiles = 0, partial_stride = 0;
@@ -219,6 +223,7 @@ struct qb_context {
     uint64_t default_workspace = uint64_t(8) << 30;  // 80 % of the memory free at creation (cudaMemGetInfo is slow: ask once)
     int64_t launches = 0;
     int64_t next_id = 1;
+    uint64_t epoch = 1;  // bumped whenever a plan or Hamiltonian is destroyed (invalidates assembled batches that may point into it)
     int l2_prefetch = 1;    // QB_L2_PREFETCH=0 switches the next-tile L2 prefetch of the sweep kernel off
     int sweep_group = 0;    // QB_SWEEP_GROUP: circuits per group (0: batch / sweep_streams)
     int sweep_streams = 2;  // QB_SWEEP_STREAMS: groups of circuits whose sweep launches run on separate streams (tail overlap)
@@ -335,6 +340,12 @@ int ensure_prefix_state(qb_context* ctx, Plan* pl) {
 int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_ids, const Ham* ham, void* external_state,
                 int init_zero, uint64_t index_offset) {
     if (batch <= 0) return fail(QB_ERR_INVALID, "batch must be positive");
+    // The same list as last time (an optimizer loop, one generation evaluated again): entries, buffers and launch shape are
+    // still valid on the device -- nothing to assemble or upload.  `epoch` moves whenever a plan or Hamiltonian is destroyed.
+    if (!external_state && b.owns_states && b.batch == batch && b.ham == ham && b.built_epoch == ctx->epoch && b.built_init_zero == init_zero &&
+        b.built_offset == index_offset && b.built_ids.size() == size_t(batch) && std::memcmp(b.built_ids.data(), plan_ids, sizeof(int64_t) * size_t(batch)) == 0)
+        return QB_OK;
+    b.built_ids.clear();
     std::vector<Plan*> plans(batch);
     for (int i = 0; i < batch; ++i) {
         plans[i] = find_plan(ctx, plan_ids[i]);
@@ -438,6 +449,10 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         std::memcpy(ctx->pin_entries.p, b.h_entries.data(), bytes);
         QB_CUDA(cudaMemcpyAsync(b.entries.p, ctx->pin_entries.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
         QB_CUDA(cudaEventRecord(ctx->pin_entries_done, ctx->stream));
+    }
+    if (!external_state) {
+        b.built_ids.assign(plan_ids, plan_ids + batch);
+        b.built_epoch = ctx->epoch, b.built_offset = index_offset, b.built_init_zero = init_zero;
     }
     return QB_OK;
 }
@@ -984,6 +999,7 @@ int qb_plan_set_prefix(qb_context* ctx, int64_t plan_id, int64_t prefix_plan_id)
         return fail(QB_ERR_INVALID, "prefix plan must be parameter-free, un-prefixed and of the same shape");
     pl->prefix_id = prefix_plan_id;
     pl->prefix_ready = false;
+    ctx->epoch++;  // assembled batches may hold this plan's old start
     return QB_OK;
 }
 
@@ -993,6 +1009,7 @@ int qb_plan_destroy(qb_context* ctx, int64_t plan_id) {
     QB_ON_DEVICE(ctx);
     cudaStreamSynchronize(ctx->stream);
     drop_single_graphs(ctx, plan_id, 0);
+    ctx->epoch++;
     return ctx->plans.erase(plan_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown plan id");
 }
 
@@ -1141,6 +1158,7 @@ int qb_hamiltonian_destroy(qb_context* ctx, int64_t ham_id) {
     QB_ON_DEVICE(ctx);
     cudaStreamSynchronize(ctx->stream);
     drop_single_graphs(ctx, 0, ham_id);
+    ctx->epoch++;
     return ctx->hams.erase(ham_id) ? QB_OK : fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
 }
 
