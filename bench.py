@@ -468,10 +468,11 @@ def guarded(fn):
 
 
 # ---------------------------------------------------------------------------------------------- extras, N = 1
-def gate_apply_probe(engine, peak):
+def gate_apply_probe(engine, peak, sizes=((24, 6), (26, 6), (28, 4), (30, 4))):
     """The sweep kernel on ONE HBM-resident state of 24 / 26 / 28 / 30 qubits (0.25 / 1 / 4 / 16 GiB), two circuits each:
       fused_evqe   a random EVQE individual: ~20 gates fused per sweep -> FP64-issue bound by design
-      hbm_regime   3 layers of 7 ``u`` gates on 7 non-low qubits behind a product start -> HBM bound
+      hbm_regime   3 layers of 7 ``u`` gates on 7 non-low qubits behind a product start -> HBM and FP64 time about equal
+      hbm_sparse   3 layers of 3 such gates -> HBM bound
     Reported for the WHOLE circuit, first (write-only, product-state) sweep included: algorithmic bytes = 16 B * 2^n for the
     first sweep + 2 * 16 B * 2^n for every later one, divided by the CUDA-event time of all sweep launches; ``rw_sweeps``
     repeats the figure for the read+write sweeps alone.  ``gates_in_sweeps`` = ops the plan really put into each sweep."""
@@ -513,7 +514,7 @@ def gate_apply_probe(engine, peak):
         return out
 
     result = {}
-    for n, layers in ((24, 6), (26, 6), (28, 4), (30, 4)):
+    for n, layers in sizes:
         ind = gn.Individual.random(n, layers, True, 7)
         fused = measure(gl.from_evqe_individual(ind), list(ind.parameter_values), 3)
         fused["layers"] = layers
@@ -524,7 +525,16 @@ def gate_apply_probe(engine, peak):
             for g in range(7):
                 circ.u(0.3 + g, 0.2 * layer, 0.1, 4 + ((g * 3 + 7 * layer) % (n - 4)))
         hbm = measure(gl.from_circuit(circ), [], 3)
-        result[f"{n}q"] = {"fused_evqe": fused, "hbm_regime": hbm}
+        # the same with 3 gates per layer: at 7 gates a sweep's FP64 work already takes as long as its HBM traffic (the write-only
+        # first sweep is as slow as the read+write ones), at 3 the traffic alone is left
+        sparse_circ = QuantumCircuit(n)
+        for q in range(n):
+            sparse_circ.u(0.1 + 0.01 * q, 0.2, 0.3, q)
+        for layer in range(3):
+            for g in range(3):
+                sparse_circ.u(0.3 + g, 0.2 * layer, 0.1, 4 + ((g * 5 + 3 * layer) % (n - 4)))
+        sparse = measure(gl.from_circuit(sparse_circ), [], 3)
+        result[f"{n}q"] = {"fused_evqe": fused, "hbm_regime": hbm, "hbm_sparse": sparse}
     return result
 
 
