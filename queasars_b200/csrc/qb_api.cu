@@ -65,19 +65,28 @@ struct DevBuf {
 struct HostBuf {  // pinned staging
     void* p = nullptr;
     size_t cap = 0;
+    bool mapped = false;  // small buffers kernels read / write directly (device alias: device_ptr())
     int reserve(size_t bytes) {
         if (bytes <= cap) return QB_OK;
         if (p) cudaFreeHost(p);  // callers synchronise on the buffer's event before growing it
         p = nullptr;
         cap = 0;
-        size_t want = std::max<size_t>(bytes, 1 << 16);
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        size_t want = std::max<size_t>(bytes, mapped ? 4096 : (1 << 16));
+        cudaError_t e = cudaHostAlloc(&p, want, mapped ? (cudaHostAllocMapped | cudaHostAllocPortable) : cudaHostAllocDefault);
         if (e != cudaSuccess) {
             cudaGetLastError();
             return fail(QB_ERR_MEMORY, std::string("cudaHostAlloc failed: ") + cudaGetErrorString(e));
         }
         cap = want;
         return QB_OK;
+    }
+    void* device_ptr() const {
+        void* d = nullptr;
+        if (!p || cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return d;
     }
     void release() {
         if (p) cudaFreeHost(p);
@@ -143,6 +152,11 @@ struct DeviceBatch {
     int64_t n_state_sweeps = 0, launches_per_run = 0;
     DevBuf entries, params, matrices, partials, out, states;
     bool owns_states = true;
+    // low-latency single-circuit path (cached CUDA graph): bind_kernel reads the parameters from, and the last reduction writes
+    // the value to, mapped pinned host memory (no copy nodes); the kernels of the chain are launched programmatically dependent
+    const double* params_mapped = nullptr;
+    double* out_mapped = nullptr;
+    bool pdl = false;
     ~DeviceBatch() {
         entries.release(), params.release(), matrices.release(), partials.release(), out.release();
         if (owns_states) states.release();
@@ -250,6 +264,8 @@ struct qb_context {
     size_t pending_results = 0;
     // single-evaluation graphs (qb_evaluate_expectation with batch == 1), least recently used evicted first
     bool use_graphs = true;  // QB_GRAPHS=0 disables
+    bool zero_copy = true;   // QB_ZERO_COPY=0: single-circuit graphs copy parameters / value with memcpy nodes instead of mapped pinned memory
+    int pdl = 1;             // QB_PDL: 0 off, 1 programmatic dependent launches inside the single-circuit graphs, 2 for every sweep chain
     std::map<std::pair<int64_t, int64_t>, std::unique_ptr<SingleGraph>> single_graphs;
     size_t single_graph_bytes = 0;
     uint64_t use_clock = 0;
@@ -297,6 +313,22 @@ int check_launch(qb_context* ctx, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QB_ERR_CUDA, std::string(what) + " launch failed: " + cudaGetErrorString(e));
     return QB_OK;
+}
+
+// Kernel launch, optionally programmatically dependent on the kernel before it in the stream (see pdl_wait() in qb_kernels.cuh).
+template <typename... KArgs, typename... Args>
+void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    if (!pdl) {
+        kernel<<<grid, block, smem, stream>>>(KArgs(args)...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);  // errors surface in check_launch
 }
 
 int upload(qb_context* ctx, DevBuf& dst, const void* src, size_t bytes) {
@@ -427,7 +459,7 @@ int build_batch(qb_context* ctx, DeviceBatch& b, int batch, const int64_t* plan_
         en.pass_ops = pl->pass_ops.as<qb_pass_op>();
         en.angles = pl->angles.as<qb_op_angles>();
         en.init_ops = pl->has_init ? pl->init_ops.as<int32_t>() : nullptr;
-        en.params = b.params.as<double>() + b.param_begin[i];
+        en.params = (b.params_mapped ? b.params_mapped : b.params.as<double>()) + b.param_begin[i];
         en.matrices = b.matrices.as<double>() + 8 * op_begin[i];
         en.state = static_cast<unsigned char*>(b.states.p) + state_bytes * size_t(pos);
         en.src_state = pl->prefix_id ? pl->prefix_state.p : nullptr;
@@ -481,6 +513,7 @@ int batch_upload_params(qb_context* ctx, DeviceBatch& b, const double* params, c
 template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context* ctx, DeviceBatch& b, cudaEvent_t* events) {
     const int flags = ctx->l2_prefetch != 0 ? qb::QB_SWEEP_L2_PREFETCH : 0;
     const int streams = events ? 1 : std::min<int>(ctx->sweep_streams, b.batch / 4);
+    const bool pdl = !events && (b.pdl || ctx->pdl >= 2);  // (event-timed runs measure every sweep on its own)
     if (streams > 1) {
         // circuits per group: by default the batch is cut into one group per stream; QB_SWEEP_GROUP = c makes groups of c circuits
         // that the streams take turns on (stream i runs groups i, i + streams, ... one after the other, each group all its sweeps
@@ -497,8 +530,8 @@ template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context
                 const int active = std::min(b.active[s], hi) - lo;  // entries are sorted by descending sweep count
                 if (active <= 0) break;
                 dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(active));
-                qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), qb::sweep_smem_bytes<T, R, K>(), st>>>(
-                    b.entries.as<qb::BatchEntry>() + lo, s, b.n_eff, fuse, b.tiles_log2, flags);
+                launch_kernel(qb::sweep_kernel<T, R, K, Idx>, grid, dim3(1 << (K - R)), qb::sweep_smem_bytes<T, R, K>(), st, pdl && s > 0,
+                              b.entries.as<qb::BatchEntry>() + lo, s, b.n_eff, fuse, b.tiles_log2, flags);
                 QB_TRY(check_launch(ctx, "sweep_kernel"));
             }
         }
@@ -512,8 +545,9 @@ template <typename T, int R, int K, typename Idx> int launch_sweeps_t(qb_context
         // every CTA stages its circuit's sweep program once and walks 2^tiles_log2 consecutive tiles with it
         dim3 grid(unsigned(b.n_tiles >> b.tiles_log2), unsigned(b.active[s]));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s], ctx->stream));
-        qb::sweep_kernel<T, R, K, Idx><<<grid, 1 << (K - R), qb::sweep_smem_bytes<T, R, K>(), ctx->stream>>>(
-            b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? (b.skip_final_store ? 2 : 1) : 0, b.tiles_log2, flags);
+        // (the first sweep follows bind_kernel in this stream)
+        launch_kernel(qb::sweep_kernel<T, R, K, Idx>, grid, dim3(1 << (K - R)), qb::sweep_smem_bytes<T, R, K>(), ctx->stream, pdl,
+                      b.entries.as<qb::BatchEntry>(), s, b.n_eff, b.fuse_expect ? (b.skip_final_store ? 2 : 1) : 0, b.tiles_log2, flags);
         QB_TRY(check_launch(ctx, "sweep_kernel"));
         if (events) QB_CUDA(cudaEventRecord(events[2 * s + 1], ctx->stream));
     }
@@ -601,17 +635,18 @@ template <typename T> int launch_expectation_t(qb_context* ctx, DeviceBatch& b) 
     const uint64_t size = uint64_t(1) << b.n_eff;
     const C* states = b.states.as<C>();
     double* partials = b.partials.as<double>();
-    double* out = b.out.as<double>();
+    double* out = b.out_mapped ? b.out_mapped : b.out.as<double>();
     bool have = false;  // does `out` already hold a value to accumulate onto?
-    auto reduce = [&](int64_t count) -> int {
-        qb::reduce_partials_kernel<<<b.batch, 256, 0, ctx->stream>>>(partials, int64_t(b.partial_stride), count, out, have ? 1 : 0);
+    auto reduce = [&](int64_t count, bool pdl = false) -> int {
+        launch_kernel(qb::reduce_partials_kernel, dim3(unsigned(b.batch)), dim3(256), 0, ctx->stream, pdl, static_cast<const double*>(partials),
+                      int64_t(b.partial_stride), count, out, have ? 1 : 0);
         have = true;
         return check_launch(ctx, "reduce_partials_kernel");
     };
     const int blocks = int(std::min<uint64_t>(1024, std::max<uint64_t>(1, size / 256)));
     // ---- diagonal part
     if (b.fuse_expect) {
-        QB_TRY(reduce(int64_t(b.n_tiles >> b.tiles_log2)));
+        QB_TRY(reduce(int64_t(b.n_tiles >> b.tiles_log2), b.pdl));  // right behind the last sweep of the chain
     } else if (ham.n_diag > 0) {
         const bool table = ham.table.p && ham.table_n_eff == b.n_eff;
         const Group* dg = ham.groups.front().get();  // the x == 0 group is stored first
@@ -656,7 +691,7 @@ template <typename T> int launch_expectation_t(qb_context* ctx, DeviceBatch& b) 
         QB_TRY(check_launch(ctx, "expect_group_kernel"));
         QB_TRY(reduce(blocks));
     }
-    if (!have) QB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * size_t(b.batch), ctx->stream));
+    if (!have) QB_TRY(reduce(0));  // no terms at all: zeros (a kernel, `out` may be mapped host memory)
     return QB_OK;
 }
 
@@ -713,32 +748,41 @@ int evaluate_single_graph(qb_context* ctx, int64_t plan_id, Plan* pl, Ham* ham, 
         }
         auto sg = std::make_unique<SingleGraph>();
         sg->state_bytes = state_bytes;
-        QB_TRY(build_batch(ctx, sg->batch, 1, &plan_id, ham, nullptr, 1, 0));  // (also computes a cached prefix state, uncaptured)
+        sg->pin_params.mapped = sg->pin_out.mapped = ctx->zero_copy;
         QB_TRY(sg->pin_params.reserve(std::max<size_t>(sizeof(double) * size_t(pl->n_params), 16)));
         QB_TRY(sg->pin_out.reserve(sizeof(double)));
-        QB_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaGraph_t graph = nullptr;
-        QB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = QB_OK;
-        if (pl->n_params && cudaMemcpyAsync(sg->batch.params.p, sg->pin_params.p, sizeof(double) * size_t(pl->n_params), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
-            rc = fail(QB_ERR_CUDA, "graph capture: parameter upload");
-        if (rc == QB_OK) rc = launch_circuits(ctx, sg->batch, nullptr);
-        if (rc == QB_OK) rc = launch_expectation(ctx, sg->batch);
-        if (rc == QB_OK && cudaMemcpyAsync(sg->pin_out.p, sg->batch.out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-            rc = fail(QB_ERR_CUDA, "graph capture: result download");
-        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-        if (rc != QB_OK || ce != cudaSuccess || !graph) {
-            if (graph) cudaGraphDestroy(graph);
-            cudaGetLastError();
-            ctx->use_graphs = false;  // capture is not available here: fall back to plain launches for good
-            return rc != QB_OK ? rc : QB_OK;
+        if (ctx->zero_copy) {
+            // no copy nodes: bind_kernel reads the (few) parameters from mapped pinned memory, the reduction writes the value there
+            sg->batch.params_mapped = static_cast<const double*>(sg->pin_params.device_ptr());
+            sg->batch.out_mapped = static_cast<double*>(sg->pin_out.device_ptr());
         }
-        ce = cudaGraphInstantiate(&sg->exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) {
-            cudaGetLastError();
-            ctx->use_graphs = false;
-            return QB_OK;
+        QB_TRY(build_batch(ctx, sg->batch, 1, &plan_id, ham, nullptr, 1, 0));  // (also computes a cached prefix state, uncaptured)
+        QB_CUDA(cudaStreamSynchronize(ctx->stream));
+        // capture: [parameter upload] -> bind -> sweeps -> reduction(s) -> [result download]; with programmatic dependent launches
+        // first, in the ordinary way if the driver refuses those inside a capture
+        for (int attempt = (ctx->pdl >= 1 ? 0 : 1); attempt < 2 && !sg->exec; ++attempt) {
+            sg->batch.pdl = attempt == 0;
+            cudaGraph_t graph = nullptr;
+            QB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = QB_OK;
+            if (pl->n_params && !sg->batch.params_mapped &&
+                cudaMemcpyAsync(sg->batch.params.p, sg->pin_params.p, sizeof(double) * size_t(pl->n_params), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                rc = fail(QB_ERR_CUDA, "graph capture: parameter upload");
+            if (rc == QB_OK) rc = launch_circuits(ctx, sg->batch, nullptr);
+            if (rc == QB_OK) rc = launch_expectation(ctx, sg->batch);
+            if (rc == QB_OK && !sg->batch.out_mapped &&
+                cudaMemcpyAsync(sg->pin_out.p, sg->batch.out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                rc = fail(QB_ERR_CUDA, "graph capture: result download");
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc == QB_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&sg->exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != QB_OK || ce != cudaSuccess) {
+                cudaGetLastError();
+                sg->exec = nullptr;
+                if (attempt == 0) continue;
+                ctx->use_graphs = false;  // capture is not available here: fall back to plain launches for good
+                return rc != QB_OK ? rc : QB_OK;
+            }
         }
         ctx->single_graph_bytes += state_bytes;
         it = ctx->single_graphs.emplace(key, std::move(sg)).first;
@@ -822,6 +866,8 @@ int qb_context_create(int device, void* stream, qb_context** out) {
     if (const char* e = std::getenv("QB_SWEEP_STREAMS")) ctx->sweep_streams = std::min(8, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("QB_SWEEP_GROUP")) ctx->sweep_group = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("QB_GRAPHS")) ctx->use_graphs = std::atoi(e) != 0;
+    if (const char* e = std::getenv("QB_PDL")) ctx->pdl = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("QB_ZERO_COPY")) ctx->zero_copy = std::atoi(e) != 0;
     if (const char* e = std::getenv("QB_L2_PREFETCH")) ctx->l2_prefetch = std::atoi(e) ? 1 : 0;
     QB_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     for (int i = 0; i < 8; ++i) {

@@ -97,14 +97,30 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
 // the compiler would otherwise treat as a generic address).  The loads are `asm volatile`: a plain asm is "pure" to the
 // compiler, which may then hoist it above the condition that guards it (seen: the diagonal-table load speculated with a
 // null table pointer).
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor in the stream still runs; everything it reads that the predecessor (or anything before it) wrote has to come
+// after pdl_wait(), which returns once the predecessor grids have completed and their writes are visible.  Both are no-ops in
+// a kernel launched the ordinary way.  Data read behind pdl_wait() is loaded with .cg (L2 only): the kernel's lifetime
+// overlaps the writes, so neither the non-coherent path nor a line left in L1 by an earlier grid may serve it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ double ld_cg(const double* p) {
+    double r;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+#ifndef QB_STATE_LD
+#define QB_STATE_LD "ld.global.cg"
+#endif
 __device__ __forceinline__ double2 ld_state(const double2* p) {
     double2 r;
-    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    asm volatile(QB_STATE_LD ".v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ float2 ld_state(const float2* p) {
     float2 r;
-    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    asm volatile(QB_STATE_LD ".v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void st_state(double2* p, double2 v) {
@@ -406,11 +422,12 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
     __shared__ double s_red[32];
     __shared__ int s_has_ext;
 
+    pdl_launch_dependents();  // a dependent launch may start its own staging now; it waits for this grid's stores in pdl_wait()
     const BatchEntry& ge = entries[blockIdx.y];
     if (sweep_idx >= ge.n_sweeps) return;
     const int tid = threadIdx.x;
 
-    // ================= staging (once per CTA) =================
+    // ================= staging (once per CTA): the sweep program first -- plan data no kernel writes =================
     if (tid < int(sizeof(qb_sweep) / 4))
         reinterpret_cast<int32_t*>(&s_sweep)[tid] = reinterpret_cast<const int32_t*>(ge.sweeps + sweep_idx)[tid];
     if (tid == 0) s_has_ext = 0;
@@ -425,14 +442,6 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
     for (int i = tid; i < n_pass * int(sizeof(qb_pass) / 4); i += kThreads)
         reinterpret_cast<int32_t*>(s_pass)[i] = reinterpret_cast<const int32_t*>(ge.passes + pass_begin)[i];
     {
-        T* s_mat_t = reinterpret_cast<T*>(s_mat);
-        const double* __restrict__ mats = ge.matrices + (size_t(ge.n_ops) + size_t(op_begin)) * 8;
-        for (int i = tid; i < n_sop * 8; i += kThreads) s_mat_t[i] = static_cast<T>(mats[i]);
-        if (product_start) {
-            T* s_init_t = reinterpret_cast<T*>(s_init);
-            const double* __restrict__ iv = ge.matrices + (size_t(ge.n_ops) + size_t(ge.n_pass_ops)) * 8;
-            for (int i = tid; i < 4 * n_eff; i += kThreads) s_init_t[i] = static_cast<T>(iv[i]);
-        }
         for (int i = tid; i <= n_sop; i += kThreads) {
             uint32_t w = 0, x = 0xffffu;
             if (i < n_sop) {
@@ -502,6 +511,19 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
 #pragma unroll
     for (int b = 0; b < K - QB_LOW_BITS; ++b) pf_off |= Idx((uint32_t(tid) >> b) & 1u) << s_sweep.tile_qubits[QB_LOW_BITS + b];
     const bool l2_prefetch = (flags & QB_SWEEP_L2_PREFETCH) && !product_start && !zero_start && tid < (1 << (K - QB_LOW_BITS));
+    // ---- from here on the kernel reads what its predecessors wrote: bound matrices (bind_kernel), the state (previous sweep)
+    pdl_wait();
+    {
+        T* s_mat_t = reinterpret_cast<T*>(s_mat);
+        const double* mats = ge.matrices + (size_t(ge.n_ops) + size_t(op_begin)) * 8;
+        for (int i = tid; i < n_sop * 8; i += kThreads) s_mat_t[i] = static_cast<T>(ld_cg(mats + i));
+        if (product_start) {
+            T* s_init_t = reinterpret_cast<T*>(s_init);
+            const double* iv = ge.matrices + (size_t(ge.n_ops) + size_t(ge.n_pass_ops)) * 8;
+            for (int i = tid; i < 4 * n_eff; i += kThreads) s_init_t[i] = static_cast<T>(ld_cg(iv + i));
+            __syncthreads();  // (CTA-uniform branch) the per-thread factor below reads s_init
+        }
+    }
     // product-state start: factor contributed by this thread's own tile bits (constant over the CTA's tiles)
     C p_thread;
     p_thread.x = T(1), p_thread.y = T(0);
@@ -935,11 +957,13 @@ expect_tile_kernel(const typename Cx<T>::type* __restrict__ states, uint64_t sta
 
 // out[b] (+)= sum_i partials[b * stride + i]  in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const double* __restrict__ partials, int64_t stride, int64_t count, double* __restrict__ out, int accumulate) {
+reduce_partials_kernel(const double* partials, int64_t stride, int64_t count, double* out, int accumulate) {
     __shared__ double s_red[8];
+    pdl_launch_dependents();
+    pdl_wait();
     const double* p = partials + blockIdx.x * stride;
     double acc = 0.0;
-    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) acc += p[i];
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) acc += ld_cg(p + i);
     const double total = block_sum(acc, s_red);
     if (threadIdx.x == 0) out[blockIdx.x] = accumulate ? out[blockIdx.x] + total : total;
 }
