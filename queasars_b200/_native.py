@@ -151,7 +151,9 @@ def pyhelper():
             lib = ctypes.PyDLL(PYHELPER_PATH)
             lib.qb_pack_rows.argtypes = [ctypes.py_object, c_void_p, c_void_p, ctypes.c_longlong]
             lib.qb_pack_rows.restype = ctypes.c_longlong
+            lib.qb_single_expectation.argtypes = [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.py_object, ctypes.c_longlong]
+            lib.qb_single_expectation.restype = ctypes.py_object
             _pyhelper = lib
-        except OSError:
+        except (OSError, AttributeError):
             _pyhelper = False
     return _pyhelper

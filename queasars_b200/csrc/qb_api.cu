@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -266,7 +267,7 @@ struct qb_context {
     bool use_graphs = true;  // QB_GRAPHS=0 disables
     bool zero_copy = true;   // QB_ZERO_COPY=0: single-circuit graphs copy parameters / value with memcpy nodes instead of mapped pinned memory
     int pdl = 1;             // QB_PDL: 0 off, 1 programmatic dependent launches inside the single-circuit graphs, 2 for every sweep chain
-    std::map<std::pair<int64_t, int64_t>, std::unique_ptr<SingleGraph>> single_graphs;
+    std::map<std::tuple<int64_t, int64_t, int>, std::unique_ptr<SingleGraph>> single_graphs;  // (plan, Hamiltonian, copies)
     size_t single_graph_bytes = 0;
     uint64_t use_clock = 0;
     std::unique_ptr<Worker> worker;  // created by the first qb_evaluate_expectation_multi that includes this context
@@ -711,9 +712,9 @@ int batch_read(qb_context* ctx, DeviceBatch& b, double* out_values) {
 
 void drop_single_graphs(qb_context* ctx, int64_t plan_id, int64_t ham_id) {
     for (auto it = ctx->single_graphs.begin(); it != ctx->single_graphs.end();) {
-        bool hit = (plan_id && it->first.first == plan_id) || (ham_id && it->first.second == ham_id);
+        bool hit = (plan_id && std::get<0>(it->first) == plan_id) || (ham_id && std::get<1>(it->first) == ham_id);
         if (!hit && plan_id) {  // a prefixed plan whose prefix goes away is rebuilt on next use as well
-            Plan* pl = find_plan(ctx, it->first.first);
+            Plan* pl = find_plan(ctx, std::get<0>(it->first));
             hit = pl && pl->prefix_id == plan_id;
         }
         if (hit) {
@@ -725,17 +726,21 @@ void drop_single_graphs(qb_context* ctx, int64_t plan_id, int64_t ham_id) {
     }
 }
 
-// qb_evaluate_expectation with batch == 1 through a cached CUDA graph.  Returns QB_OK with *handled = false when the graph path
-// does not apply (disabled, state too large to keep resident per circuit).
-int evaluate_single_graph(qb_context* ctx, int64_t plan_id, Plan* pl, Ham* ham, int64_t ham_id, const double* params, int64_t n_params,
-                          double* out_value, bool* handled) {
+// qb_evaluate_expectation of ONE circuit at 1 .. kMaxGraphCopies parameter points (the optimizer loop's calls: SPSA evaluates
+// theta +- c delta together) through a cached CUDA graph.  Returns QB_OK with *handled = false when the graph path does not
+// apply (disabled, states too large to keep resident per circuit).
+constexpr int kMaxGraphCopies = 4;  // (from 8 entries on the sweep launches fork into stream groups)
+int evaluate_single_graph(qb_context* ctx, int64_t plan_id, Plan* pl, Ham* ham, int64_t ham_id, int copies, const double* params,
+                          const int64_t* param_offsets, double* out_values, bool* handled) {
     *handled = false;
-    const size_t state_bytes = (size_t(1) << pl->n_eff) * amp_bytes(pl->dtype);
+    const size_t state_bytes = (size_t(1) << pl->n_eff) * amp_bytes(pl->dtype) * size_t(copies);
     const size_t budget = std::min<size_t>(size_t(4) << 30, (ctx->workspace_limit ? ctx->workspace_limit : ctx->default_workspace) / 8);
     if (!ctx->use_graphs || state_bytes > budget / 4) return QB_OK;
-    if (n_params != pl->n_params)
-        return fail(QB_ERR_INVALID, "entry 0: got " + std::to_string(n_params) + " parameter values, circuit has " + std::to_string(pl->n_params) + " parameters");
-    const auto key = std::make_pair(plan_id, ham_id);
+    for (int i = 0; i < copies; ++i)
+        if (param_offsets[i + 1] - param_offsets[i] != pl->n_params)
+            return fail(QB_ERR_INVALID, "entry " + std::to_string(i) + ": got " + std::to_string(param_offsets[i + 1] - param_offsets[i]) +
+                                            " parameter values, circuit has " + std::to_string(pl->n_params) + " parameters");
+    const auto key = std::make_tuple(plan_id, ham_id, copies);
     auto it = ctx->single_graphs.find(key);
     if (it == ctx->single_graphs.end()) {
         while (!ctx->single_graphs.empty() && (ctx->single_graph_bytes + state_bytes > budget || ctx->single_graphs.size() >= 256)) {
@@ -749,14 +754,16 @@ int evaluate_single_graph(qb_context* ctx, int64_t plan_id, Plan* pl, Ham* ham, 
         auto sg = std::make_unique<SingleGraph>();
         sg->state_bytes = state_bytes;
         sg->pin_params.mapped = sg->pin_out.mapped = ctx->zero_copy;
-        QB_TRY(sg->pin_params.reserve(std::max<size_t>(sizeof(double) * size_t(pl->n_params), 16)));
-        QB_TRY(sg->pin_out.reserve(sizeof(double)));
+        const size_t params_bytes = sizeof(double) * size_t(pl->n_params) * size_t(copies), out_bytes = sizeof(double) * size_t(copies);
+        QB_TRY(sg->pin_params.reserve(std::max<size_t>(params_bytes, 16)));
+        QB_TRY(sg->pin_out.reserve(out_bytes));
         if (ctx->zero_copy) {
             // no copy nodes: bind_kernel reads the (few) parameters from mapped pinned memory, the reduction writes the value there
             sg->batch.params_mapped = static_cast<const double*>(sg->pin_params.device_ptr());
             sg->batch.out_mapped = static_cast<double*>(sg->pin_out.device_ptr());
         }
-        QB_TRY(build_batch(ctx, sg->batch, 1, &plan_id, ham, nullptr, 1, 0));  // (also computes a cached prefix state, uncaptured)
+        const std::vector<int64_t> ids(size_t(copies), plan_id);
+        QB_TRY(build_batch(ctx, sg->batch, copies, ids.data(), ham, nullptr, 1, 0));  // (also computes a cached prefix state, uncaptured)
         QB_CUDA(cudaStreamSynchronize(ctx->stream));
         // capture: [parameter upload] -> bind -> sweeps -> reduction(s) -> [result download]; with programmatic dependent launches
         // first, in the ordinary way if the driver refuses those inside a capture
@@ -766,12 +773,12 @@ int evaluate_single_graph(qb_context* ctx, int64_t plan_id, Plan* pl, Ham* ham, 
             QB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             int rc = QB_OK;
             if (pl->n_params && !sg->batch.params_mapped &&
-                cudaMemcpyAsync(sg->batch.params.p, sg->pin_params.p, sizeof(double) * size_t(pl->n_params), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                cudaMemcpyAsync(sg->batch.params.p, sg->pin_params.p, params_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
                 rc = fail(QB_ERR_CUDA, "graph capture: parameter upload");
             if (rc == QB_OK) rc = launch_circuits(ctx, sg->batch, nullptr);
             if (rc == QB_OK) rc = launch_expectation(ctx, sg->batch);
             if (rc == QB_OK && !sg->batch.out_mapped &&
-                cudaMemcpyAsync(sg->pin_out.p, sg->batch.out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                cudaMemcpyAsync(sg->pin_out.p, sg->batch.out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
                 rc = fail(QB_ERR_CUDA, "graph capture: result download");
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
             if (rc == QB_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&sg->exec, graph, 0);
@@ -789,11 +796,13 @@ int evaluate_single_graph(qb_context* ctx, int64_t plan_id, Plan* pl, Ham* ham, 
     }
     SingleGraph& sg = *it->second;
     sg.last_use = ++ctx->use_clock;
-    if (pl->n_params) std::memcpy(sg.pin_params.p, params, sizeof(double) * size_t(pl->n_params));
+    for (int i = 0; i < copies && pl->n_params; ++i)  // entry i's parameters live at param_begin[i] (caller order)
+        std::memcpy(static_cast<double*>(sg.pin_params.p) + sg.batch.param_begin[i], params + param_offsets[i], sizeof(double) * size_t(pl->n_params));
     QB_CUDA(cudaGraphLaunch(sg.exec, ctx->stream));
     ctx->launches += sg.batch.max_sweeps + 2;  // bind + sweeps + reduction(s), as counted for plain launches
     QB_CUDA(cudaStreamSynchronize(ctx->stream));
-    *out_value = *static_cast<const double*>(sg.pin_out.p);
+    const volatile double* sorted = static_cast<const volatile double*>(sg.pin_out.p);
+    for (int pos = 0; pos < copies; ++pos) out_values[sg.batch.order[pos]] = sorted[pos];
     *handled = true;
     return QB_OK;
 }
@@ -1345,9 +1354,10 @@ int qb_evaluate_expectation(qb_context* ctx, int batch, const int64_t* plan_ids,
     if (!ham) return fail(QB_ERR_NOT_FOUND, "unknown Hamiltonian id");
     Plan* first = find_plan(ctx, plan_ids[0]);
     if (!first) return fail(QB_ERR_NOT_FOUND, "unknown plan id " + std::to_string(plan_ids[0]));
-    if (batch == 1) {  // the optimizer loop's call: replay the evaluation's CUDA graph
+    if (batch <= kMaxGraphCopies && std::all_of(plan_ids, plan_ids + batch, [&](int64_t id) { return id == plan_ids[0]; })) {
+        // the optimizer loop's call (one circuit, one or a few parameter points): replay the evaluation's CUDA graph
         bool handled = false;
-        QB_TRY(evaluate_single_graph(ctx, plan_ids[0], first, ham, ham_id, params + param_offsets[0], param_offsets[1] - param_offsets[0], out_values, &handled));
+        QB_TRY(evaluate_single_graph(ctx, plan_ids[0], first, ham, ham_id, batch, params, param_offsets, out_values, &handled));
         if (handled) return QB_OK;
     }
     const int chunk = int(std::min<size_t>(size_t(batch), max_batch_for(ctx, first)));

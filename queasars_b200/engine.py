@@ -154,6 +154,7 @@ class Engine:
         handle = c_void_p()
         _native.check(self._lib.qb_context_create(self.device, c_void_p(stream) if stream else None, byref(handle)))
         self._ctx = handle
+        self._eval_fn = ctypes.cast(self._lib.qb_evaluate_expectation, c_void_p)  # handed to the marshalling helper
         self._lock = threading.Lock()
         self._plan_cache: dict = {}
         self._prefix_bytes = 0
@@ -352,6 +353,17 @@ class Engine:
             return np.zeros(0)
         if len(plans) != len(params):
             raise ValueError(f"{len(plans)} circuits but {len(params)} parameter vectors")
+        if len(plans) == 1:  # the optimizer loop's call: one native-helper call packs the row and evaluates it
+            row, plan = params[0], plans[0]
+            helper = _native.pyhelper() if type(row) in (list, tuple) else None
+            if helper:
+                r = helper.qb_single_expectation(self._eval_fn, self._ctx, plan.plan_id, plan.n_params, row, ham.ham_id)
+                if type(r) is float:
+                    return np.array((r,))
+                if r == -1000:
+                    raise ValueError(f"circuit 0 has {plan.n_params} parameters but {len(row)} values were given")
+                if r != -2000:  # (-2000: a row the helper cannot read -- the NumPy path below decides)
+                    _native.check(r)
         out = np.empty(len(plans), dtype=np.float64)
         split = self._pipeline_split(plans, params)
         if split is None:

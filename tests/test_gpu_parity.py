@@ -588,7 +588,8 @@ def test_term_counts_beyond_the_shared_memory_staging(engine):
 
 
 def test_single_circuit_calls_replay_a_cuda_graph(engine):
-    """Batch-1 calls (the optimizer loop: mutation.py:63-75) go through a cached CUDA graph per (plan, Hamiltonian): same values
+    """Calls with one circuit at 1-4 parameter points (the optimizer loop: mutation.py:63-75) go through a cached CUDA graph per
+    (plan, Hamiltonian, points): same values
     as the batched path for changing parameter values, for prefixed plans, and after the plan / Hamiltonian are destroyed and
     rebuilt (the cached graph must go with them)."""
     import gc
@@ -606,6 +607,12 @@ def test_single_circuit_calls_replay_a_cuda_graph(engine):
             single = [engine.expectation([plan], [r], ham)[0] for r in rows]
             batched = engine.expectation([plan] * 6, rows, ham)
             np.testing.assert_allclose(single, batched, rtol=0, atol=1e-12)
+            # one circuit at 2 / 3 / 4 parameter points (SPSA's theta +- c delta): graph path as well, rows given as lists and as a block
+            for copies in (2, 3, 4):
+                np.testing.assert_allclose(engine.expectation([plan] * copies, rows[:copies], ham), batched[:copies], rtol=0, atol=1e-12)
+                np.testing.assert_allclose(engine.expectation([plan] * copies, np.asarray(rows[1 : copies + 1]), ham), batched[1 : copies + 1], rtol=0, atol=1e-12)
+            with pytest.raises(Exception):
+                engine.expectation([plan] * 2, [rows[0], rows[1][:-1]], ham)
             table = oq.diagonal_table(n, oq.diag_terms_from_labels(terms))
             assert rel_err(single[0], float(np.dot(np.abs(oq.statevector(instr, n, rows[0])) ** 2, table))) < 1e-10
             with pytest.raises(Exception):

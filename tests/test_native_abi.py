@@ -79,3 +79,42 @@ def test_list_marshalling_helper_matches_numpy():
         Engine._pack(plans, rows[:2] + [rows[2][:2]] + rows[3:])
     with pytest.raises((ValueError, TypeError)):
         Engine._pack(plans, rows[:3] + [["x"] * 11])
+
+
+def test_single_evaluation_helper_marshals_and_passes_status_through():
+    """qb_single_expectation (csrc/qb_pyhelper.c): the one-circuit call of the optimizer loop.  Checked against a stand-in for
+    qb_evaluate_expectation with the same C signature (no GPU here): arguments as the C-ABI defines them, value returned as a
+    Python float, native status / length error / unreadable row reported as ints."""
+    import ctypes
+
+    from queasars_b200 import _build, _native
+
+    _build.build_pyhelper()
+    helper = _native.pyhelper()
+    assert helper, "helper library not loadable"
+    seen = {}
+
+    @ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double),
+                      ctypes.POINTER(ctypes.c_longlong), ctypes.c_longlong, ctypes.POINTER(ctypes.c_double))
+    def fake_eval(ctx, batch, ids, params, offsets, ham_id, out):
+        n = offsets[1] - offsets[0]
+        seen.update(ctx=ctx, batch=batch, plan=ids[0], first=offsets[0], n=n, ham=ham_id)
+        if ham_id == 99:
+            return _native.QB_ERR_NOT_FOUND
+        out[0] = sum(params[i] * (i + 1) for i in range(n)) + 0.5
+        return 0
+
+    fn = ctypes.cast(fake_eval, ctypes.c_void_p)
+    ctx = ctypes.c_void_p(0x1234)
+    row = [0.25, 2, -1.5]  # an int among the floats
+    r = helper.qb_single_expectation(fn, ctx, 42, 3, row, 7)
+    assert type(r) is float and r == 0.25 + 2 * 2 - 1.5 * 3 + 0.5
+    assert seen == {"ctx": 0x1234, "batch": 1, "plan": 42, "first": 0, "n": 3, "ham": 7}
+    assert helper.qb_single_expectation(fn, ctx, 42, 3, tuple(row), 7) == r
+    assert helper.qb_single_expectation(fn, ctx, 42, 0, [], 7) == 0.5  # parameter-free circuit
+    long_row = [float(i) for i in range(700)]  # beyond the helper's stack buffer
+    assert helper.qb_single_expectation(fn, ctx, 1, 700, long_row, 7) == sum(v * (i + 1) for i, v in enumerate(long_row)) + 0.5
+    assert helper.qb_single_expectation(fn, ctx, 42, 4, row, 7) == -1000  # wrong length
+    assert helper.qb_single_expectation(fn, ctx, 42, 3, ["x", 1.0, 2.0], 7) == -2000  # not numbers: NumPy path decides
+    assert helper.qb_single_expectation(fn, ctx, 42, 3, 5, 7) == -2000  # not a sequence
+    assert helper.qb_single_expectation(fn, ctx, 42, 3, row, 99) == _native.QB_ERR_NOT_FOUND  # native status passed through
