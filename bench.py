@@ -14,7 +14,8 @@ synthetic random diagonal Ising Hamiltonian (20 Z + 190 ZZ terms, default_rng(12
 Extras on rank 0 at N = 1 (``--skip-extras`` drops them): ``gate_apply`` (sweep kernel on ONE 24/26/28/30-qubit state, whole
 circuit incl. the write-only first sweep), ``cpu_baseline`` (C/OpenMP oracle port on the host cores), ``c3_24q_tfim``,
 ``c4_26q_sampler`` (BASELINE configs 3 and 4 through the evaluators, with the error against the C oracle), ``e2e_threaded``
-(the reference's calling pattern: 32 threads x single-circuit calls).
+(the reference's calling pattern: 32 threads x single-circuit calls), ``optimizer_calls`` (one circuit, one or two parameter points
+per call, last layer parameterised: microseconds per call).
 Multi-GPU (torchrun, one process per GPU): the headline is WEAK scaling -- every rank evaluates the same population of 32, no
 data-path collective.  Extras at N > 1: ``strong`` (ONE population of 32 split over the N ranks + an all-gather of the 32
 doubles per step), ``api_all_devices`` (ONE process driving all N GPUs through ``B200EstimatorV2(devices="all")``, the
@@ -442,6 +443,7 @@ def run_b200(args):
             line["c3_24q_tfim"] = guarded(lambda: c3_probe(local_rank))
             line["c4_26q_sampler"] = guarded(lambda: c4_probe(local_rank))
             line["e2e_threaded"] = guarded(lambda: threaded_probe(local_rank, operator, circuits, params, values, args))
+            line["optimizer_calls"] = guarded(lambda: optimizer_calls_probe(local_rank, operator, individuals))
             line["c1_jssp_reference_loop"] = guarded(lambda: c1_probe(local_rank))
             line["c2_complex64"] = guarded(lambda: complex64_probe(local_rank, operator, circuits, params, values, args))
         else:
@@ -683,6 +685,43 @@ def complex64_probe(device, operator, circuits, params, values, args):
         ev.evaluate_circuits(circuits, params)
     dt = time.perf_counter() - t0
     return {"evals_per_s": POPULATION * reps / dt, "ms_per_call": 1e3 * dt / reps, "max_rel_err_vs_complex128": err, "tolerance": 1e-4}
+
+
+def optimizer_calls_probe(device, operator, individuals):
+    """The optimizer loop's calling pattern (mutation.py:59-77: SPSA / NFT evaluate ONE circuit with only its last layer
+    parameterised at one or two points per call, sequentially): microseconds per call through the evaluator
+    (``evaluate_circuits([circuit] * k, rows)``, prefix-state reuse and the cached CUDA graph behind it) and at the engine level,
+    for the last-layer circuit and for the fully parameterised one.  20 qubits, the headline Hamiltonian."""
+    from queasars_b200 import B200EstimatorV2, B200OperatorCircuitEvaluator
+    from queasars_b200 import gate_list as gl
+
+    ind = individuals[0]
+    est = B200EstimatorV2(device=device, dtype="complex128", coalesce=False)
+    ev = B200OperatorCircuitEvaluator(est, 0.0, operator)
+    engine = est.engines[0] if hasattr(est, "engines") else est.engine
+    ham = engine.hamiltonian(operator)
+    rng = np.random.default_rng(5)
+    out = {"n_qubits": ind.n_qubits, "layers": len(ind.layers)}
+    for name, layers in (("last_layer", {-1}), ("all_layers", None)):
+        circuit = ind.to_circuit(layers)
+        gates = gl.from_evqe_individual(ind, layers)
+        plan = engine.compile_with_prefix_reuse(gates, drop_final_phases=True) if layers else engine.compile(gates, drop_final_phases=True)
+        for points in (1, 2):
+            rows = [list(rng.uniform(0, 6.28, gates.n_params)) for _ in range(points)]
+            res = {}
+            for label, call in (("evaluator_us_per_call", lambda: ev.evaluate_circuits([circuit] * points, rows)),
+                                ("engine_us_per_call", lambda: engine.expectation([plan] * points, rows, ham))):
+                for _ in range(30):
+                    call()
+                reps = 500
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    call()
+                res[label] = 1e6 * (time.perf_counter() - t0) / reps
+            want = engine.expectation([plan] * points, rows, ham)
+            res["evaluator_matches_engine"] = bool(np.allclose(ev.evaluate_circuits([circuit] * points, rows), want, rtol=0, atol=1e-12))
+            out[f"{name}_{points}pt"] = res
+    return out
 
 
 def threaded_probe(device, operator, circuits, params, values, args):

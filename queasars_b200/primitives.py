@@ -443,8 +443,14 @@ class B200EstimatorV2(_B200Primitive):
         if not circuits:
             return np.zeros(0)
         fp = _operator_fingerprint(operator)  # once per call: guards the cached device Hamiltonian against in-place edits
-        if not self._needs_sharding(int(operator.num_qubits)):
-            self.hamiltonian_for(operator, fingerprint=fp)  # validates the operator (and builds its device form) before anything is queued
+        sharded = self._needs_sharding(int(operator.num_qubits))
+        if not sharded:
+            ham = self.hamiltonian_for(operator, fingerprint=fp)  # validates the operator (and builds its device form) before anything is queued
+            engines = self._engines_obj  # (built by the calls above)
+            if not self.coalesce and len(engines) == 1:
+                # one device, nothing to merge with other threads' requests (the optimizer loop's sequential calls): straight to the engine
+                resolved = self._resolve_all(circuits, parameter_values, probabilities_only=ham.diagonal)
+                return np.asarray(engines[0].expectation([r[1] for r in resolved], [r[2] for r in resolved], ham), dtype=np.float64)
         return np.asarray(self._submit(("exp", id(operator), fp), (operator, circuits, parameter_values)))
 
     def _execute(self, key, payloads):

@@ -46,14 +46,16 @@ def terms_for(n):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("devices", [None, "all"])
-def test_operator_evaluator_host_flow(fake_engines, devices):
+@pytest.mark.parametrize("devices,coalesce", [(None, True), ("all", True), (None, False), ("all", False)])
+def test_operator_evaluator_host_flow(fake_engines, devices, coalesce):
+    """(coalesce=False on one device is the direct engine call of the optimizer loop; every other combination goes through
+    the queue / the device split)"""
     from queasars_b200.evaluators import B200OperatorCircuitEvaluator
 
     n = 5
     terms = terms_for(n)
     op = SparsePauliOp.from_list(terms)
-    est = pr.B200EstimatorV2(devices=devices, coalesce=True)
+    est = pr.B200EstimatorV2(devices=devices, coalesce=coalesce)
     ev = B200OperatorCircuitEvaluator(est, 0.0, op)
     cases = [case(n, 2, s) for s in range(7)]
     got = ev.evaluate_circuits([c for _, _, c in cases], [v for _, v, _ in cases])
