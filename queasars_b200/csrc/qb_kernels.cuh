@@ -110,6 +110,9 @@ __device__ __forceinline__ double ld_cg(const double* p) {
     return r;
 }
 
+#ifndef QB_PLAIN_FAST
+#define QB_PLAIN_FAST 1
+#endif
 #ifndef QB_STATE_LD
 #define QB_STATE_LD "ld.global.cg"
 #endif
@@ -351,10 +354,12 @@ __device__ __forceinline__ void apply_op(uint32_t word, uint32_t e_thr, typename
     // The common cases are reached by predictable branches instead of the jump table (+2 %), the commonest first: an
     // uncontrolled dense gate with a real first column (variants 48 + b: every `u` of an EVQE circuit after phase deferral),
     // then one with a real top-left entry only (bit 5 of the variant).
+#if !QB_PLAIN_FAST
     if ((variant ^ 48u) < uint32_t(R)) {
         dense_by_bit<T, R, true, true>(variant & 3u, a, m);
         return;
     }
+#endif
     if ((variant ^ 32u) < uint32_t(R)) {
         dense_by_bit<T, R, true>(variant & 3u, a, m);
         return;
@@ -457,7 +462,13 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                     if (ang.slot[0] < 0 && ang.slot2[0] < 0 && ang.cnst[0] == 0.0) {
                         variant |= 32u;  // gamma == 0: m00 = cos(theta / 2) is real
                         // phi == 0 too: m10 = sin(theta / 2) is real (uncontrolled gates only have such bodies)
+#if QB_PLAIN_FAST
+                        // (only for gates without a control of any kind: those bodies are reached from the op loop directly;
+                        //  the rare thread-bit- or externally controlled gate with phi == 0 runs the real-top-left body)
+                        if (rcb < 0 && cpos == 31 && extc == 0xff && ang.slot[2] < 0 && ang.slot2[2] < 0 && ang.cnst[2] == 0.0) variant |= 16u;
+#else
                         if (rcb < 0 && ang.slot[2] < 0 && ang.slot2[2] < 0 && ang.cnst[2] == 0.0) variant |= 16u;
+#endif
                     }
                 } else {
                     if (po.tgt_kind == QB_K_THREAD) dpos = po.tgt_pos;
@@ -473,6 +484,11 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                     }
                 }
                 w = variant | (cpos << 6) | (dpos << 11) | (cb << 17) | (tb << 20) | (treg << 23);
+#if QB_PLAIN_FAST
+                // bit 31: the commonest op -- a dense gate with a real first column and no control of any kind (variant 48 + b);
+                // the op loop reaches its body through one sign test and the two bits of b, without the control test
+                if (po.kind == QB_OP_DENSE && (variant ^ 48u) < uint32_t(R)) w |= 0x80000000u;
+#endif
                 x = extc | (extt << 8);
                 if (x != 0xffffu) s_has_ext = 1;
             }
@@ -658,6 +674,12 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
             for (; o < o_end; ++o) {
                 const uint32_t word = word_next;
                 word_next = s_w[o + 1];  // prefetch the next dispatch word behind this op's arithmetic
+#if QB_PLAIN_FAST
+                if (int32_t(word) < 0) {
+                    dense_by_bit<T, R, true, true>(word & 3u, a, s_mat + o * 4);
+                    continue;
+                }
+#endif
                 if (!((test >> ((word >> 6) & 31u)) & 1u)) continue;
                 apply_op<T, R>(word, e_thr, a, s_mat + o * 4);
             }
