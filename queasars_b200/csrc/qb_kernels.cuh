@@ -113,6 +113,9 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 #ifndef QB_PLAIN_FAST
 #define QB_PLAIN_FAST 1
 #endif
+#ifndef QB_PLAIN_PRELOAD
+#define QB_PLAIN_PRELOAD 0
+#endif
 #ifndef QB_STATE_LD
 #define QB_STATE_LD "ld.global.cg"
 #endif
@@ -319,6 +322,24 @@ __device__ __forceinline__ void dense_by_bit(uint32_t v, typename Cx<T>::type (&
     } else {
         if (v & 1u) dense_if<T, R, 1, -1, REAL00, REAL10>(a, m);
         else dense_if<T, R, 0, -1, REAL00, REAL10>(a, m);
+    }
+}
+
+// the same for the op loop's direct path (real first column), matrix entries already in registers: their shared-memory loads
+// are issued before the two branches instead of behind them
+template <typename T, int R>
+__device__ __forceinline__ void plain_by_bit(uint32_t v, typename Cx<T>::type (&a)[1 << R], const typename Cx<T>::type m00, const typename Cx<T>::type m01,
+                                             const typename Cx<T>::type m10, const typename Cx<T>::type m11) {
+    if (v & 2u) {
+        if constexpr (R > 3) {
+            if (v & 1u) apply_dense<T, R, 3, -1, true, true>(a, m00, m01, m10, m11);
+            else apply_dense<T, R, 2, -1, true, true>(a, m00, m01, m10, m11);
+        } else {
+            apply_dense<T, R, 2, -1, true, true>(a, m00, m01, m10, m11);
+        }
+    } else {
+        if (v & 1u) apply_dense<T, R, 1, -1, true, true>(a, m00, m01, m10, m11);
+        else apply_dense<T, R, 0, -1, true, true>(a, m00, m01, m10, m11);
     }
 }
 
@@ -676,7 +697,14 @@ sweep_kernel(const BatchEntry* __restrict__ entries, int sweep_idx, int n_eff, i
                 word_next = s_w[o + 1];  // prefetch the next dispatch word behind this op's arithmetic
 #if QB_PLAIN_FAST
                 if (int32_t(word) < 0) {
+#if QB_PLAIN_PRELOAD
+                    const C* m = s_mat + o * 4;
+                    C m00, m10;
+                    m00.x = m[0].x, m00.y = T(0), m10.x = m[2].x, m10.y = T(0);  // (real entries: the imaginary parts are never read)
+                    plain_by_bit<T, R>(word & 3u, a, m00, m[1], m10, m[3]);
+#else
                     dense_by_bit<T, R, true, true>(word & 3u, a, s_mat + o * 4);
+#endif
                     continue;
                 }
 #endif
