@@ -306,6 +306,8 @@ struct DeviceScope {
 
 template <typename K> int configure_kernel(K kernel, size_t smem) {
     QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    // QB_SMEM_CARVEOUT = 0..100: preferred shared-memory share of the SM's unified L1 / shared storage (default: the driver's choice)
+    if (const char* e = std::getenv("QB_SMEM_CARVEOUT")) QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e)));
     return QB_OK;
 }
 
