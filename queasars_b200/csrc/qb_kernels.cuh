@@ -116,6 +116,9 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 #ifndef QB_PLAIN_PRELOAD
 #define QB_PLAIN_PRELOAD 0
 #endif
+#ifndef QB_TABLE_LD
+#define QB_TABLE_LD "ld.global.nc.f64"
+#endif
 #ifndef QB_STATE_LD
 #define QB_STATE_LD "ld.global.cg"
 #endif
@@ -137,7 +140,7 @@ __device__ __forceinline__ void st_state(float2* p, float2 v) {
 }
 __device__ __forceinline__ double ld_table(const double* p) {
     double r;
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    asm volatile(QB_TABLE_LD " %0, [%1];" : "=d"(r) : "l"(p));
     return r;
 }
 
